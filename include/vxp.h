@@ -1,0 +1,120 @@
+/*
+ * vxp.h — C ABI of libvxp.so: B200 (sm_100a) chunk terrain fill and meshing.
+ *
+ * Boundary note.  The reference snapshot (voxelphile/voxelphile, crate
+ * `xenotech`) exposes NO interface for this path: its only public items are
+ * `xenotech::main` (src/lib.rs:9), the login enums (src/lib.rs:31-45) and
+ * `User` (src/lib.rs:47); `client()`/`server()` (src/lib.rs:109,111), where a
+ * world/mesher would attach, are empty.  There is therefore nothing for these
+ * entry points to "replace"; they define the boundary that a
+ * Rust `extern "C"` block would bind — see INTEGRATION.md and rust/vxp-sys.
+ * The one convention carried over is the reference's payload-free error kinds
+ * returned by value (src/net/udp/mod.rs:16-28): every call returns a
+ * vxp_status and nothing throws across the ABI.
+ *
+ * Semantics of every buffer and bit are fixed by SPEC.md (v1).
+ * There is no CPU fallback: without a CUDA device every call fails.
+ *
+ * Threading: a vxp_ctx is used by one thread at a time; distinct contexts (one
+ * per GPU) may be driven concurrently.  Device-level calls are asynchronous on
+ * the context's stream; host-level calls synchronise before returning.
+ */
+#ifndef VXP_H
+#define VXP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VXP_SPEC_VERSION 1
+#define VXP_CHUNK_DIM 32
+#define VXP_CHUNK_VOXELS 32768
+#define VXP_MAX_QUADS_PER_CHUNK 98304
+
+typedef struct vxp_ctx vxp_ctx;
+
+typedef enum vxp_status {
+    VXP_OK = 0,
+    VXP_ERR_BAD_ARG = 1,
+    VXP_ERR_NO_DEVICE = 2,
+    VXP_ERR_OOM = 3,
+    VXP_ERR_CAPACITY = 4, /* output arena too small; total_quads holds the need */
+    VXP_ERR_CUDA = 5
+} vxp_status;
+
+typedef enum vxp_mode { VXP_MODE_CULLED = 0, VXP_MODE_GREEDY = 1 } vxp_mode;
+typedef enum vxp_pattern { VXP_PATTERN_CHECKER = 0, VXP_PATTERN_SOLID4 = 1 } vxp_pattern;
+
+typedef struct vxp_coord { int32_t x, y, z; } vxp_coord;           /* chunk coordinate */
+typedef struct vxp_chunk_meta { uint32_t first_quad, quad_count; } vxp_chunk_meta;
+
+/* Batch mesh in DEVICE memory (SPEC §5).  All four arrays are caller-owned. */
+typedef struct vxp_mesh_dev {
+    uint64_t *verts;          /* 4 * capacity_quads vertices, 8 B each        */
+    uint32_t *indices;        /* 6 * capacity_quads indices                    */
+    vxp_chunk_meta *meta;     /* n entries                                     */
+    uint64_t *total_quads;    /* one counter; zeroed by the call               */
+    uint64_t capacity_quads;
+} vxp_mesh_dev;
+
+/* Batch mesh in HOST memory, owned by the context (pinned); valid until the
+ * next host-level call on the same context or vxp_ctx_destroy. */
+typedef struct vxp_mesh_host {
+    const uint64_t *verts;
+    const uint32_t *indices;
+    const vxp_chunk_meta *meta;
+    uint64_t total_quads;
+} vxp_mesh_host;
+
+/* ---- context ----------------------------------------------------------- */
+vxp_status vxp_ctx_create(int device, vxp_ctx **out);
+void vxp_ctx_destroy(vxp_ctx *ctx);
+/* Run device-level calls on the caller's CUDA stream (a cudaStream_t); NULL
+ * restores the context's own stream. */
+vxp_status vxp_ctx_set_stream(vxp_ctx *ctx, void *cuda_stream);
+vxp_status vxp_ctx_synchronize(vxp_ctx *ctx);
+const char *vxp_status_str(vxp_status s);
+/* Detail of the last VXP_ERR_CUDA on this context ("" if none). */
+const char *vxp_last_error(const vxp_ctx *ctx);
+/* Kernels launched by this context since creation (bench bookkeeping). */
+uint64_t vxp_launch_count(const vxp_ctx *ctx);
+int vxp_spec_version(void);
+
+/* ---- host helpers (no device work) ------------------------------------- */
+/* nbr[i][f] = index of the chunk at coords[i] + dir_f, or -1 (SPEC §1). */
+vxp_status vxp_nbr6_from_coords(const vxp_coord *coords, uint32_t n, int32_t *nbr6);
+/* Pinned host memory for the host-level calls' inputs. */
+vxp_status vxp_host_alloc(size_t bytes, void **out);
+void vxp_host_free(void *p);
+
+/* ---- device level: every pointer is device memory ---------------------- */
+/* SPEC §6: d_voxels[i] = terrain of chunk d_coords[i]. */
+vxp_status vxp_terrain_fill_batch(vxp_ctx *ctx, const vxp_coord *d_coords, uint32_t n,
+                                  uint64_t seed, uint16_t *d_voxels);
+/* SPEC §7 test patterns. */
+vxp_status vxp_pattern_fill_batch(vxp_ctx *ctx, const vxp_coord *d_coords, uint32_t n,
+                                  vxp_pattern pattern, uint16_t *d_voxels);
+/* SPEC §2-§5: mesh n stored chunks.  d_nbr6 may be NULL (all sides air).
+ * Overflow of out->capacity_quads is only visible in *out->total_quads and
+ * meta[i].first_quad == 0xFFFFFFFF (the call itself is asynchronous). */
+vxp_status vxp_mesh_batch(vxp_ctx *ctx, const uint16_t *d_voxels, const int32_t *d_nbr6,
+                          uint32_t n, vxp_mode mode, const vxp_mesh_dev *out);
+/* Terrain + mesh without materialising voxels: chunk d_coords[i] is meshed
+ * against the infinite terrain of `seed` (all six neighbours are terrain). */
+vxp_status vxp_terrain_mesh_fused(vxp_ctx *ctx, const vxp_coord *d_coords, uint32_t n,
+                                  uint64_t seed, vxp_mode mode, const vxp_mesh_dev *out);
+
+/* ---- host level: host pointers in, context-owned pinned results out ---- */
+vxp_status vxp_terrain_fill_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
+                                 uint64_t seed, uint16_t *voxels);
+vxp_status vxp_mesh_chunks_host(vxp_ctx *ctx, const uint16_t *voxels, const int32_t *nbr6,
+                                uint32_t n, vxp_mode mode, vxp_mesh_host *out);
+vxp_status vxp_terrain_mesh_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
+                                 uint64_t seed, vxp_mode mode, vxp_mesh_host *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VXP_H */

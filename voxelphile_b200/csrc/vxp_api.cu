@@ -1,0 +1,390 @@
+// vxp_api.cu — the C ABI of libvxp.so (include/vxp.h).  Thin: argument checks, context-owned
+// arenas for the host-level calls, launches.  No CPU fallback anywhere: every compute entry
+// point ends in a kernel launch or an error.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/vxp.h"
+#include "vxp_launch.h"
+
+struct vxp_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    std::string last_error;
+
+    // arenas of the host-level calls (grown on demand, never shrunk)
+    uint16_t* d_voxels = nullptr;   size_t voxels_cap = 0;   // chunks
+    int32_t* d_nbr6 = nullptr;      size_t nbr_cap = 0;      // chunks
+    vxp_coord* d_coords = nullptr;  size_t coords_cap = 0;   // chunks
+    vxp_chunk_meta* d_meta = nullptr; size_t meta_cap = 0;   // chunks
+    uint64_t* d_verts = nullptr;    uint32_t* d_indices = nullptr; size_t quads_cap = 0;
+    uint64_t* d_total = nullptr;
+    vxp_chunk_meta* h_meta = nullptr; size_t h_meta_cap = 0;
+    uint64_t* h_verts = nullptr;    uint32_t* h_indices = nullptr; size_t h_quads_cap = 0;
+    uint64_t* h_total = nullptr;
+};
+
+namespace {
+
+vxp_status cuda_fail(vxp_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    if (e == cudaErrorMemoryAllocation) return VXP_ERR_OOM;
+    return VXP_ERR_CUDA;
+}
+#define VXP_CUDA(ctx, expr)                                        \
+    do {                                                           \
+        cudaError_t e__ = (expr);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #expr); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <class T>
+vxp_status grow_device(vxp_ctx* ctx, T** p, size_t* cap, size_t need, size_t elems_per_unit) {
+    if (need <= *cap) return VXP_OK;
+    size_t want = need + need / 4;
+    if (*p) VXP_CUDA(ctx, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(p), want * elems_per_unit * sizeof(T)));
+    *cap = want;
+    return VXP_OK;
+}
+template <class T>
+vxp_status grow_pinned(vxp_ctx* ctx, T** p, size_t* cap, size_t need, size_t elems_per_unit) {
+    if (need <= *cap) return VXP_OK;
+    size_t want = need + need / 4;
+    if (*p) VXP_CUDA(ctx, cudaFreeHost(*p));
+    *p = nullptr;
+    *cap = 0;
+    VXP_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(p), want * elems_per_unit * sizeof(T)));
+    *cap = want;
+    return VXP_OK;
+}
+
+vxp_status grow_quads(vxp_ctx* ctx, size_t need) {
+    if (need <= ctx->quads_cap) return VXP_OK;
+    size_t want = need + need / 4;
+    if (ctx->d_verts) VXP_CUDA(ctx, cudaFree(ctx->d_verts));
+    if (ctx->d_indices) VXP_CUDA(ctx, cudaFree(ctx->d_indices));
+    ctx->d_verts = nullptr;
+    ctx->d_indices = nullptr;
+    ctx->quads_cap = 0;
+    VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_verts), want * 4 * sizeof(uint64_t)));
+    VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_indices), want * 6 * sizeof(uint32_t)));
+    ctx->quads_cap = want;
+    return VXP_OK;
+}
+vxp_status grow_host_quads(vxp_ctx* ctx, size_t need) {
+    if (need <= ctx->h_quads_cap) return VXP_OK;
+    size_t want = need + need / 4;
+    if (ctx->h_verts) VXP_CUDA(ctx, cudaFreeHost(ctx->h_verts));
+    if (ctx->h_indices) VXP_CUDA(ctx, cudaFreeHost(ctx->h_indices));
+    ctx->h_verts = nullptr;
+    ctx->h_indices = nullptr;
+    ctx->h_quads_cap = 0;
+    VXP_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_verts), want * 4 * sizeof(uint64_t)));
+    VXP_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_indices), want * 6 * sizeof(uint32_t)));
+    ctx->h_quads_cap = want;
+    return VXP_OK;
+}
+
+bool valid_mode(vxp_mode m) { return m == VXP_MODE_CULLED || m == VXP_MODE_GREEDY; }
+
+bool valid_out(const vxp_mesh_dev* o, uint32_t n) {
+    if (!o || !o->total_quads) return false;
+    if (n && !o->meta) return false;
+    if (o->capacity_quads && (!o->verts || !o->indices)) return false;
+    if (!aligned16(o->verts) || (reinterpret_cast<uintptr_t>(o->indices) & 7u)) return false;
+    if (o->capacity_quads > 0xFFFFFFFEull) return false;  // first_quad is a u32; 0xFFFFFFFF is the overflow mark
+    return true;
+}
+
+// Run one mesh launch into the context's arena, growing it until the result fits; download.
+template <class Launch>
+vxp_status mesh_into_host(vxp_ctx* ctx, uint32_t n, Launch launch, vxp_mesh_host* out) {
+    vxp_status s;
+    if ((s = grow_device(ctx, &ctx->d_meta, &ctx->meta_cap, n, 1)) != VXP_OK) return s;
+    if ((s = grow_pinned(ctx, &ctx->h_meta, &ctx->h_meta_cap, n, 1)) != VXP_OK) return s;
+    if ((s = grow_quads(ctx, (size_t)n * 64 + 4096)) != VXP_OK) return s;  // first guess; grows below
+    uint64_t total = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        vxp_mesh_dev dev{ctx->d_verts, ctx->d_indices, ctx->d_meta, ctx->d_total, ctx->quads_cap};
+        VXP_CUDA(ctx, launch(dev));
+        ctx->launches += n ? 1 : 0;
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_total, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        total = *ctx->h_total;
+        if (total <= ctx->quads_cap) break;
+        if (attempt == 2) return VXP_ERR_CAPACITY;
+        if ((s = grow_quads(ctx, total)) != VXP_OK) return s;
+    }
+    if ((s = grow_host_quads(ctx, total)) != VXP_OK) return s;
+    if (n)
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_meta, ctx->d_meta, (size_t)n * sizeof(vxp_chunk_meta),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    if (total) {
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_verts, ctx->d_verts, total * 4 * sizeof(uint64_t),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices, ctx->d_indices, total * 6 * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->verts = ctx->h_verts;
+    out->indices = ctx->h_indices;
+    out->meta = ctx->h_meta;
+    out->total_quads = total;
+    return VXP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vxp_spec_version(void) { return VXP_SPEC_VERSION; }
+
+const char* vxp_status_str(vxp_status s) {
+    switch (s) {
+        case VXP_OK: return "ok";
+        case VXP_ERR_BAD_ARG: return "bad argument";
+        case VXP_ERR_NO_DEVICE: return "no CUDA device (libvxp has no CPU fallback)";
+        case VXP_ERR_OOM: return "out of memory";
+        case VXP_ERR_CAPACITY: return "output capacity exceeded";
+        case VXP_ERR_CUDA: return "CUDA error";
+    }
+    return "unknown status";
+}
+
+vxp_status vxp_ctx_create(int device, vxp_ctx** out) {
+    if (!out) return VXP_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return VXP_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return VXP_ERR_BAD_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VXP_ERR_CUDA;
+    if (prop.major != 10) return VXP_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    vxp_ctx* ctx = new (std::nothrow) vxp_ctx();
+    if (!ctx) return VXP_ERR_OOM;
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = vxp::configure_device();
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_total), sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_total), sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        vxp_status s = cuda_fail(nullptr, e, "ctx_create");
+        vxp_ctx_destroy(ctx);
+        return s;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return VXP_OK;
+}
+
+void vxp_ctx_destroy(vxp_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    cudaFree(ctx->d_voxels);
+    cudaFree(ctx->d_nbr6);
+    cudaFree(ctx->d_coords);
+    cudaFree(ctx->d_meta);
+    cudaFree(ctx->d_verts);
+    cudaFree(ctx->d_indices);
+    cudaFree(ctx->d_total);
+    cudaFreeHost(ctx->h_meta);
+    cudaFreeHost(ctx->h_verts);
+    cudaFreeHost(ctx->h_indices);
+    cudaFreeHost(ctx->h_total);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+vxp_status vxp_ctx_set_stream(vxp_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return VXP_ERR_BAD_ARG;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return VXP_OK;
+}
+
+vxp_status vxp_ctx_synchronize(vxp_ctx* ctx) {
+    if (!ctx) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VXP_OK;
+}
+
+const char* vxp_last_error(const vxp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t vxp_launch_count(const vxp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+vxp_status vxp_nbr6_from_coords(const vxp_coord* coords, uint32_t n, int32_t* nbr6) {
+    if (n && (!coords || !nbr6)) return VXP_ERR_BAD_ARG;
+    auto key = [](int32_t x, int32_t y, int32_t z) {
+        return (uint64_t)((uint32_t)x & 0x1FFFFFu) | (uint64_t)((uint32_t)y & 0x1FFFFFu) << 21 |
+               (uint64_t)((uint32_t)z & 0x1FFFFFu) << 42;
+    };
+    const int32_t lim = 1 << 20;
+    std::unordered_map<uint64_t, int32_t> index;
+    try {
+        index.reserve((size_t)n * 2);
+        for (uint32_t i = 0; i < n; ++i) {
+            const vxp_coord c = coords[i];
+            if (c.x < -lim + 1 || c.x >= lim - 1 || c.y < -lim + 1 || c.y >= lim - 1 || c.z < -lim + 1 ||
+                c.z >= lim - 1)
+                return VXP_ERR_BAD_ARG;
+            if (!index.emplace(key(c.x, c.y, c.z), (int32_t)i).second) return VXP_ERR_BAD_ARG;  // duplicate
+        }
+    } catch (const std::bad_alloc&) {
+        return VXP_ERR_OOM;
+    }
+    static const int d[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+    for (uint32_t i = 0; i < n; ++i)
+        for (int f = 0; f < 6; ++f) {
+            auto it = index.find(key(coords[i].x + d[f][0], coords[i].y + d[f][1], coords[i].z + d[f][2]));
+            nbr6[6 * (size_t)i + f] = it == index.end() ? -1 : it->second;
+        }
+    return VXP_OK;
+}
+
+vxp_status vxp_host_alloc(size_t bytes, void** out) {
+    if (!out) return VXP_ERR_BAD_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? VXP_ERR_OOM : VXP_ERR_NO_DEVICE;
+    }
+    return VXP_OK;
+}
+void vxp_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ device level
+
+vxp_status vxp_terrain_fill_batch(vxp_ctx* ctx, const vxp_coord* d_coords, uint32_t n, uint64_t seed,
+                                  uint16_t* d_voxels) {
+    if (!ctx || (n && (!d_coords || !d_voxels)) || !aligned16(d_voxels)) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    VXP_CUDA(ctx, vxp::launch_terrain_fill(d_coords, n, seed, d_voxels, ctx->stream));
+    ctx->launches += n ? 1 : 0;
+    return VXP_OK;
+}
+
+vxp_status vxp_pattern_fill_batch(vxp_ctx* ctx, const vxp_coord* d_coords, uint32_t n, vxp_pattern pattern,
+                                  uint16_t* d_voxels) {
+    if (!ctx || (n && (!d_coords || !d_voxels)) || !aligned16(d_voxels)) return VXP_ERR_BAD_ARG;
+    if (pattern != VXP_PATTERN_CHECKER && pattern != VXP_PATTERN_SOLID4) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    VXP_CUDA(ctx, vxp::launch_pattern_fill(d_coords, n, (int)pattern, d_voxels, ctx->stream));
+    ctx->launches += n ? 1 : 0;
+    return VXP_OK;
+}
+
+vxp_status vxp_mesh_batch(vxp_ctx* ctx, const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n,
+                          vxp_mode mode, const vxp_mesh_dev* out) {
+    if (!ctx || !valid_mode(mode) || !valid_out(out, n)) return VXP_ERR_BAD_ARG;
+    if (n && (!d_voxels || !aligned16(d_voxels))) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    VXP_CUDA(ctx, vxp::launch_mesh(d_voxels, d_nbr6, n, mode == VXP_MODE_GREEDY, *out, ctx->stream));
+    ctx->launches += n ? 1 : 0;
+    return VXP_OK;
+}
+
+vxp_status vxp_terrain_mesh_fused(vxp_ctx* ctx, const vxp_coord* d_coords, uint32_t n, uint64_t seed,
+                                  vxp_mode mode, const vxp_mesh_dev* out) {
+    if (!ctx || !valid_mode(mode) || !valid_out(out, n) || (n && !d_coords)) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    VXP_CUDA(ctx, vxp::launch_terrain_mesh(d_coords, n, seed, mode == VXP_MODE_GREEDY, *out, ctx->stream));
+    ctx->launches += n ? 1 : 0;
+    return VXP_OK;
+}
+
+// ------------------------------------------------------------------ host level
+
+vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t n, uint64_t seed,
+                                 uint16_t* voxels) {
+    if (!ctx || (n && (!coords || !voxels))) return VXP_ERR_BAD_ARG;
+    if (n == 0) return VXP_OK;
+    DeviceGuard g(ctx->device);
+    vxp_status s;
+    if ((s = grow_device(ctx, &ctx->d_coords, &ctx->coords_cap, n, 1)) != VXP_OK) return s;
+    if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
+    VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_coords, coords, (size_t)n * sizeof(vxp_coord), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    VXP_CUDA(ctx, vxp::launch_terrain_fill(ctx->d_coords, n, seed, ctx->d_voxels, ctx->stream));
+    ctx->launches += 1;
+    VXP_CUDA(ctx, cudaMemcpyAsync(voxels, ctx->d_voxels, (size_t)n * VXP_CHUNK_VOXELS * sizeof(uint16_t),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VXP_OK;
+}
+
+vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int32_t* nbr6, uint32_t n,
+                                vxp_mode mode, vxp_mesh_host* out) {
+    if (!ctx || !out || !valid_mode(mode) || (n && !voxels)) return VXP_ERR_BAD_ARG;
+    if (nbr6)
+        for (size_t i = 0; i < (size_t)n * 6; ++i)
+            if (nbr6[i] < -1 || nbr6[i] >= (int64_t)n) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    vxp_status s;
+    if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
+    if ((s = grow_device(ctx, &ctx->d_nbr6, &ctx->nbr_cap, n, 6)) != VXP_OK) return s;
+    if (n) {
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels, voxels, (size_t)n * VXP_CHUNK_VOXELS * sizeof(uint16_t),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        if (nbr6)
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int32_t* d_nbr = nbr6 ? ctx->d_nbr6 : nullptr;
+    return mesh_into_host(
+        ctx, n,
+        [&](const vxp_mesh_dev& dev) {
+            return vxp::launch_mesh(ctx->d_voxels, d_nbr, n, mode == VXP_MODE_GREEDY, dev, ctx->stream);
+        },
+        out);
+}
+
+vxp_status vxp_terrain_mesh_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t n, uint64_t seed,
+                                 vxp_mode mode, vxp_mesh_host* out) {
+    if (!ctx || !out || !valid_mode(mode) || (n && !coords)) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    vxp_status s;
+    if ((s = grow_device(ctx, &ctx->d_coords, &ctx->coords_cap, n, 1)) != VXP_OK) return s;
+    if (n)
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_coords, coords, (size_t)n * sizeof(vxp_coord),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    return mesh_into_host(
+        ctx, n,
+        [&](const vxp_mesh_dev& dev) {
+            return vxp::launch_terrain_mesh(ctx->d_coords, n, seed, mode == VXP_MODE_GREEDY, dev, ctx->stream);
+        },
+        out);
+}
+
+}  // extern "C"

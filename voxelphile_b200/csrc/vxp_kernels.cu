@@ -1,0 +1,268 @@
+// vxp_kernels.cu — sm_100a kernels: terrain fill, pattern fill, stored-chunk meshing,
+// fused terrain+mesh.  SPEC.md v1.  Host launchers at the bottom (C++ linkage, used by vxp_api.cu).
+#include <climits>
+
+#include "vxp_launch.h"
+#include "vxp_mesh.cuh"
+
+namespace vxp {
+
+// ====================================================================== terrain fill (SPEC §6)
+// One CTA per chunk: 1024 column heights -> shared memory, then 4096 16-byte stores.
+__global__ void __launch_bounds__(kThreads) terrain_fill_kernel(const vxp_coord* __restrict__ coords, uint32_t n,
+                                                                 uint64_t seed, uint16_t* __restrict__ out) {
+    __shared__ int s_h[1024];
+    __shared__ int s_red[2 * kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TerrainKeys tk = terrain_keys(seed);
+    for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const vxp_coord c = coords[chunk];
+        int hmin = INT_MAX, hmax = INT_MIN;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = tid + k * kThreads; // col = z*32 + x
+            const int h = terrain_height(tk, 32 * c.x + (col & 31), 32 * c.z + (col >> 5));
+            s_h[col] = h;
+            hmin = min(hmin, h);
+            hmax = max(hmax, h);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            hmin = min(hmin, __shfl_xor_sync(kFull, hmin, d));
+            hmax = max(hmax, __shfl_xor_sync(kFull, hmax, d));
+        }
+        if (lane == 0) { s_red[warp] = hmin; s_red[kWarps + warp] = hmax; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kWarps + w]); }
+
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)chunk * VXP_CHUNK_VOXELS);
+        const int Y0 = 32 * c.y;
+        if (Y0 > hmax) {                       // whole chunk above the surface: air
+#pragma unroll 4
+            for (int j = tid; j < 4096; j += kThreads) dst[j] = make_uint4(0, 0, 0, 0);
+        } else if (Y0 + 31 < hmin - 3) {       // whole chunk below the dirt: stone/slate bands by Y only
+#pragma unroll 4
+            for (int j = tid; j < 4096; j += kThreads) {
+                const int Y = Y0 + ((j >> 2) & 31);
+                const uint32_t b = ((Y >> 3) & 1) ? 4u : 3u;
+                const uint32_t bb = b | b << 16;
+                dst[j] = make_uint4(bb, bb, bb, bb);
+            }
+        } else {
+#pragma unroll 2
+            for (int j = tid; j < 4096; j += kThreads) { // j = (z*32 + y)*4 + p
+                const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
+                const int* hp = s_h + z * 32 + x0;
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
+                dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ====================================================================== pattern fill (SPEC §7)
+__global__ void __launch_bounds__(kThreads) pattern_fill_kernel(const vxp_coord* __restrict__ coords, uint32_t n,
+                                                                 int pattern, uint16_t* __restrict__ out) {
+    const int tid = threadIdx.x;
+    for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const vxp_coord c = coords[chunk];
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)chunk * VXP_CHUNK_VOXELS);
+        for (int j = tid; j < 4096; j += kThreads) {
+            const int Z = 32 * c.z + (j >> 7), Y = 32 * c.y + ((j >> 2) & 31), X0 = 32 * c.x + (j & 3) * 8;
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                w[e] = pattern_block(pattern, X0 + 2 * e, Y, Z) | pattern_block(pattern, X0 + 2 * e + 1, Y, Z) << 16;
+            dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+// ====================================================================== stored-chunk meshing
+// v1: one CTA per chunk, the tile staged by one bulk TMA; two CTAs per SM overlap load and compute.
+template <bool kGreedy>
+__global__ void __launch_bounds__(kThreads, 2)
+mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, MeshOut out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MeshSmem& sm = *reinterpret_cast<MeshSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= n) return;
+    const uint16_t* gvox = voxels + (size_t)chunk * VXP_CHUNK_VOXELS;
+
+    if (tid == 0) {
+        sm.ones = kFull;
+        mbar_init(&sm.mbar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(&sm.mbar, kTileBytes);
+        tma_load_1d(sm.tile.vox, gvox, kTileBytes, &sm.mbar);
+    }
+    load_halo(sm, voxels, nbr6, chunk);     // overlaps the TMA
+    __syncthreads();                        // barrier init visible to all waiters
+    mbar_wait(&sm.mbar, 0);
+
+    const bool uniform = build_occupancy(sm);   // contains a block barrier: occ + halos published
+    if (uniform && sm.tile.vox[0] == 0) {       // all air: no faces
+        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+        return;
+    }
+    if (kGreedy && !uniform) build_equality(sm);
+    __syncthreads();                            // tile is dead from here on (aliased by ht/vt/staging)
+    build_masks<kGreedy>(sm, uniform);
+    __syncthreads();
+    emit_chunk<kGreedy>(sm, chunk, uniform, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); });
+}
+
+// ====================================================================== fused terrain + mesh
+// The tile is generated in shared memory from the height field; voxels never reach HBM.
+template <bool kGreedy>
+__global__ void __launch_bounds__(kThreads, 2)
+terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t seed, MeshOut out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MeshSmem& sm = *reinterpret_cast<MeshSmem*>(smem_raw);
+    __shared__ int s_h[34 * 34];   // heights of the 34x34 column footprint: s_h[(z+1)*34 + (x+1)]
+    __shared__ int s_red[2 * kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= n) return;
+    const vxp_coord c = coords[chunk];
+    const TerrainKeys tk = terrain_keys(seed);
+    if (tid == 0) sm.ones = kFull;
+
+    int hmin = INT_MAX, hmax = INT_MIN;
+    for (int i = tid; i < 34 * 34; i += kThreads) {
+        const int zz = i / 34 - 1, xx = i % 34 - 1;
+        const bool corner = (zz < 0 || zz > 31) && (xx < 0 || xx > 31);
+        int h = 0;
+        if (!corner) {
+            h = terrain_height(tk, 32 * c.x + xx, 32 * c.z + zz);
+            hmin = min(hmin, h);
+            hmax = max(hmax, h);
+        }
+        s_h[i] = h;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        hmin = min(hmin, __shfl_xor_sync(kFull, hmin, d));
+        hmax = max(hmax, __shfl_xor_sync(kFull, hmax, d));
+    }
+    if (lane == 0) { s_red[warp] = hmin; s_red[kWarps + warp] = hmax; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kWarps + w]); }
+
+    const int Y0 = 32 * c.y;
+    // all air (incl. the layer below it) or all solid incl. every halo layer: no visible face
+    if (Y0 > hmax || Y0 + 32 <= hmin) {
+        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+        return;
+    }
+    // tile
+    uint4* tile4 = reinterpret_cast<uint4*>(sm.tile.vox);
+#pragma unroll 2
+    for (int j = tid; j < 4096; j += kThreads) {
+        const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
+        const int* hp = s_h + (z + 1) * 34 + x0 + 1;
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
+        tile4[j] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    // halo occupancy straight from the heights (solid iff Y <= h)
+    for (int i = tid; i < 128; i += kThreads) {       // Y and Z halo rows: word over x
+        const int face = i >> 5, r = i & 31;          // 0:-Y 1:+Y 2:-Z 3:+Z
+        int zz, Y, dst;
+        if (face == 0) { zz = r; Y = Y0 - 1; dst = (r + 1) * 34 + 0; }
+        else if (face == 1) { zz = r; Y = Y0 + 32; dst = (r + 1) * 34 + 33; }
+        else if (face == 2) { zz = -1; Y = Y0 + r; dst = 0 * 34 + (r + 1); }
+        else { zz = 32; Y = Y0 + r; dst = 33 * 34 + (r + 1); }
+        const int* hp = s_h + (zz + 1) * 34 + 1;
+        uint32_t bits = 0;
+#pragma unroll 8
+        for (int x = 0; x < 32; ++x) bits |= (uint32_t)(Y <= hp[x]) << x;
+        sm.occ[dst] = bits;
+    }
+    if (tid < 64) {                                   // X halos: word over y for each z
+        const int face = tid >> 5, z = tid & 31;
+        const int h = s_h[(z + 1) * 34 + (face ? 33 : 0)];
+        uint32_t bits = 0;
+#pragma unroll 8
+        for (int y = 0; y < 32; ++y) bits |= (uint32_t)(Y0 + y <= h) << y;
+        sm.xh[face][z] = bits;
+    }
+    __syncthreads();
+
+    const bool uniform = build_occupancy(sm);
+    if (kGreedy && !uniform) build_equality(sm);
+    __syncthreads();
+    build_masks<kGreedy>(sm, uniform);
+    __syncthreads();
+    const int* hcol = s_h;
+    emit_chunk<kGreedy>(sm, chunk, uniform, out, [hcol, Y0](int idx) -> uint32_t {
+        const int x = idx & 31, y = (idx >> 5) & 31, z = idx >> 10;
+        return terrain_block(hcol[(z + 1) * 34 + x + 1], Y0 + y);
+    });
+}
+
+// ====================================================================== launchers
+
+static cudaError_t set_smem(const void* fn) {
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem));
+}
+
+cudaError_t configure_device() {
+    cudaError_t e = set_smem((const void*)mesh_kernel<false>);
+    if (e == cudaSuccess) e = set_smem((const void*)mesh_kernel<true>);
+    if (e == cudaSuccess) e = set_smem((const void*)terrain_mesh_kernel<false>);
+    if (e == cudaSuccess) e = set_smem((const void*)terrain_mesh_kernel<true>);
+    return e;
+}
+
+cudaError_t launch_terrain_fill(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
+                                cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    terrain_fill_kernel<<<n, kThreads, 0, stream>>>(d_coords, n, seed, d_voxels);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pattern_fill(const vxp_coord* d_coords, uint32_t n, int pattern, uint16_t* d_voxels,
+                                cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    pattern_fill_kernel<<<n, kThreads, 0, stream>>>(d_coords, n, pattern, d_voxels);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, int greedy,
+                        const vxp_mesh_dev& o, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
+    if (e != cudaSuccess || n == 0) return e;
+    MeshOut out{reinterpret_cast<unsigned long long*>(o.verts), o.indices, o.meta,
+                reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads};
+    if (greedy)
+        mesh_kernel<true><<<n, kThreads, sizeof(MeshSmem), stream>>>(d_voxels, d_nbr6, n, out);
+    else
+        mesh_kernel<false><<<n, kThreads, sizeof(MeshSmem), stream>>>(d_voxels, d_nbr6, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_terrain_mesh(const vxp_coord* d_coords, uint32_t n, uint64_t seed, int greedy,
+                                const vxp_mesh_dev& o, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
+    if (e != cudaSuccess || n == 0) return e;
+    MeshOut out{reinterpret_cast<unsigned long long*>(o.verts), o.indices, o.meta,
+                reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads};
+    if (greedy)
+        terrain_mesh_kernel<true><<<n, kThreads, sizeof(MeshSmem), stream>>>(d_coords, n, seed, out);
+    else
+        terrain_mesh_kernel<false><<<n, kThreads, sizeof(MeshSmem), stream>>>(d_coords, n, seed, out);
+    return cudaGetLastError();
+}
+
+size_t mesh_smem_bytes() { return sizeof(MeshSmem); }
+
+} // namespace vxp

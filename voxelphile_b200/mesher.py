@@ -1,0 +1,250 @@
+"""Host-side chunk / mesher surface over the C ABI (include/vxp.h).
+
+The reference snapshot defines no chunk or mesher API (its only public items are
+``xenotech::main``, the login enums and ``User`` — src/lib.rs:9,31-47), so this
+module defines the surface the Rust crate in ``rust/vxp`` mirrors: chunk
+coordinate -> voxel array -> mesh buffers.  Errors follow the reference's
+payload-free enum style (src/net/udp/mod.rs:16-28): ``MeshError.kind`` is one of
+a fixed set of names and carries no payload beyond the library's detail string.
+
+PyTorch is used only to own device memory and streams; all compute is in
+libvxp.so (hand-written sm_100a kernels).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+CULLED, GREEDY = _lib.MODE_CULLED, _lib.MODE_GREEDY
+CHUNK_DIM = 32
+CHUNK_VOXELS = _lib.CHUNK_VOXELS
+
+_KINDS = {
+    _lib.VXP_ERR_BAD_ARG: "BadArg",
+    _lib.VXP_ERR_NO_DEVICE: "NoDevice",
+    _lib.VXP_ERR_OOM: "OutOfMemory",
+    _lib.VXP_ERR_CAPACITY: "Capacity",
+    _lib.VXP_ERR_CUDA: "Cuda",
+}
+
+
+class MeshError(RuntimeError):
+    """Payload-free error kind (``BadArg | NoDevice | OutOfMemory | Capacity | Cuda``)."""
+
+    def __init__(self, status: int, detail: str = ""):
+        self.status = status
+        self.kind = _KINDS.get(status, "Unknown")
+        super().__init__(f"{self.kind}: {detail}" if detail else self.kind)
+
+
+def neighbour_table(coords: np.ndarray) -> np.ndarray:
+    """``nbr[i][f]`` = index of the chunk at ``coords[i] + dir_f`` or -1 (SPEC §1). Host-only."""
+    coords = np.ascontiguousarray(coords, dtype=np.int32).reshape(-1, 3)
+    nbr = np.empty((coords.shape[0], 6), dtype=np.int32)
+    st = _lib.load().vxp_nbr6_from_coords(coords.ctypes.data, coords.shape[0], nbr.ctypes.data)
+    if st != _lib.VXP_OK:
+        raise MeshError(st, "neighbour_table")
+    return nbr
+
+
+def grid_coords(lo, hi) -> np.ndarray:
+    """Chunk coordinates of the box [lo, hi) in x-fastest order, as int32 [n,3]."""
+    lo, hi = np.asarray(lo), np.asarray(hi)
+    z, y, x = np.meshgrid(np.arange(lo[2], hi[2]), np.arange(lo[1], hi[1]), np.arange(lo[0], hi[0]), indexing="ij")
+    return np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1).astype(np.int32)
+
+
+@dataclass
+class DeviceMesh:
+    """Batch mesh in device memory (SPEC §5). ``verts`` holds u64 bit patterns in int64."""
+
+    verts: "torch.Tensor"    # int64 [4*capacity]
+    indices: "torch.Tensor"  # int32 [6*capacity]
+    meta: "torch.Tensor"     # int32 [n,2]  (first_quad, quad_count)
+    total: "torch.Tensor"    # int64 [1]
+    capacity: int
+
+    def to_host(self) -> "HostMesh":
+        total = int(self.total.item())
+        if total > self.capacity:
+            raise MeshError(_lib.VXP_ERR_CAPACITY, f"need {total} quads, capacity {self.capacity}")
+        return HostMesh(
+            verts=self.verts[: 4 * total].cpu().numpy().view(np.uint64),
+            indices=self.indices[: 6 * total].cpu().numpy().view(np.uint32),
+            meta=self.meta.cpu().numpy().view(np.uint32).reshape(-1, 2),
+            total_quads=total,
+        )
+
+
+@dataclass
+class HostMesh:
+    verts: np.ndarray    # uint64 [4*Q]
+    indices: np.ndarray  # uint32 [6*Q]
+    meta: np.ndarray     # uint32 [n,2]
+    total_quads: int
+
+    def chunk(self, i: int):
+        """(verts[cnt,4], indices[cnt,6]) of chunk i."""
+        first, cnt = int(self.meta[i, 0]), int(self.meta[i, 1])
+        return (self.verts[4 * first : 4 * (first + cnt)].reshape(cnt, 4),
+                self.indices[6 * first : 6 * (first + cnt)].reshape(cnt, 6))
+
+
+class Mesher:
+    """One context = one GPU = one stream.  Mirrors ``vxp_ctx`` 1:1."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self.device = device
+        h = C.c_void_p()
+        st = self._lib.vxp_ctx_create(device, C.byref(h))
+        if st != _lib.VXP_OK:
+            raise MeshError(st, self._lib.vxp_status_str(st).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vxp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != _lib.VXP_OK:
+            detail = self._lib.vxp_last_error(self._h).decode() if st == _lib.VXP_ERR_CUDA else \
+                self._lib.vxp_status_str(st).decode()
+            raise MeshError(st, detail)
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.vxp_launch_count(self._h))
+
+    def use_stream(self, stream: Optional["torch.cuda.Stream"]):
+        self._check(self._lib.vxp_ctx_set_stream(self._h, stream.cuda_stream if stream is not None else None))
+
+    def use_current_torch_stream(self):
+        import torch
+        self.use_stream(torch.cuda.current_stream(self.device))
+
+    def synchronize(self):
+        self._check(self._lib.vxp_ctx_synchronize(self._h))
+
+    # ------------------------------------------------------------ device level (torch tensors)
+    def _dev(self):
+        import torch
+        return torch.device("cuda", self.device)
+
+    def alloc_mesh(self, n: int, capacity: int) -> DeviceMesh:
+        import torch
+        d = self._dev()
+        return DeviceMesh(
+            verts=torch.empty(4 * max(capacity, 1), dtype=torch.int64, device=d),
+            indices=torch.empty(6 * max(capacity, 1), dtype=torch.int32, device=d),
+            meta=torch.zeros((n, 2), dtype=torch.int32, device=d),
+            total=torch.zeros(1, dtype=torch.int64, device=d),
+            capacity=capacity,
+        )
+
+    @staticmethod
+    def _mesh_struct(m: DeviceMesh) -> _lib.MeshDev:
+        return _lib.MeshDev(m.verts.data_ptr(), m.indices.data_ptr(), m.meta.data_ptr(), m.total.data_ptr(),
+                            m.capacity)
+
+    def terrain_fill(self, coords: "torch.Tensor", seed: int, out: Optional["torch.Tensor"] = None):
+        """coords: int32 [n,3] on this device -> int16 [n,32768] (u16 bit patterns)."""
+        import torch
+        n = coords.shape[0]
+        assert coords.dtype == torch.int32 and coords.is_contiguous() and coords.is_cuda
+        if out is None:
+            out = torch.empty((n, CHUNK_VOXELS), dtype=torch.int16, device=coords.device)
+        self._check(self._lib.vxp_terrain_fill_batch(self._h, coords.data_ptr(), n, seed & (2**64 - 1),
+                                                     out.data_ptr()))
+        return out
+
+    def pattern_fill(self, coords: "torch.Tensor", pattern: int, out: Optional["torch.Tensor"] = None):
+        import torch
+        n = coords.shape[0]
+        assert coords.dtype == torch.int32 and coords.is_contiguous() and coords.is_cuda
+        if out is None:
+            out = torch.empty((n, CHUNK_VOXELS), dtype=torch.int16, device=coords.device)
+        self._check(self._lib.vxp_pattern_fill_batch(self._h, coords.data_ptr(), n, pattern, out.data_ptr()))
+        return out
+
+    def mesh(self, voxels: "torch.Tensor", nbr6: Optional["torch.Tensor"], mode: int,
+             out: Optional[DeviceMesh] = None, capacity: Optional[int] = None) -> DeviceMesh:
+        """voxels: 16-bit [n,32768] device tensor; nbr6: int32 [n,6] or None. Asynchronous."""
+        n = voxels.shape[0]
+        assert voxels.is_cuda and voxels.is_contiguous() and voxels.element_size() == 2
+        if nbr6 is not None:
+            assert nbr6.is_cuda and nbr6.is_contiguous() and nbr6.shape == (n, 6)
+        if out is None:
+            out = self.alloc_mesh(n, capacity if capacity is not None else n * 1024)
+        s = self._mesh_struct(out)
+        self._check(self._lib.vxp_mesh_batch(self._h, voxels.data_ptr(),
+                                             nbr6.data_ptr() if nbr6 is not None else None, n, mode, C.byref(s)))
+        return out
+
+    def terrain_mesh(self, coords: "torch.Tensor", seed: int, mode: int, out: Optional[DeviceMesh] = None,
+                     capacity: Optional[int] = None) -> DeviceMesh:
+        n = coords.shape[0]
+        if out is None:
+            out = self.alloc_mesh(n, capacity if capacity is not None else n * 256)
+        s = self._mesh_struct(out)
+        self._check(self._lib.vxp_terrain_mesh_fused(self._h, coords.data_ptr(), n, seed & (2**64 - 1), mode,
+                                                     C.byref(s)))
+        return out
+
+    # ------------------------------------------------------------ host level (numpy in, numpy out)
+    def _host_result(self, h: _lib.MeshHost, n: int, copy: bool) -> HostMesh:
+        q = int(h.total_quads)
+
+        def view(ptr, count, dtype):
+            if count == 0:
+                return np.empty(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            a = np.frombuffer(buf, dtype=dtype, count=count)
+            return a.copy() if copy else a
+
+        return HostMesh(view(h.verts, 4 * q, np.uint64), view(h.indices, 6 * q, np.uint32),
+                        view(h.meta, 2 * n, np.uint32).reshape(n, 2), q)
+
+    def mesh_host(self, voxels: np.ndarray, nbr6: Optional[np.ndarray], mode: int, copy: bool = True) -> HostMesh:
+        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call)."""
+        voxels = np.ascontiguousarray(voxels, dtype=np.uint16).reshape(-1, CHUNK_VOXELS)
+        n = voxels.shape[0]
+        nptr = None
+        if nbr6 is not None:
+            nbr6 = np.ascontiguousarray(nbr6, dtype=np.int32).reshape(n, 6)
+            nptr = nbr6.ctypes.data
+        h = _lib.MeshHost()
+        self._check(self._lib.vxp_mesh_chunks_host(self._h, voxels.ctypes.data, nptr, n, mode, C.byref(h)))
+        return self._host_result(h, n, copy)
+
+    def mesh_host_ptr(self, voxels_ptr: int, nbr6_ptr: Optional[int], n: int, mode: int) -> HostMesh:
+        """Same, from raw (e.g. pinned) host pointers; the result aliases context-owned pinned memory."""
+        h = _lib.MeshHost()
+        self._check(self._lib.vxp_mesh_chunks_host(self._h, voxels_ptr, nbr6_ptr, n, mode, C.byref(h)))
+        return self._host_result(h, n, copy=False)
+
+    def terrain_mesh_host(self, coords: np.ndarray, seed: int, mode: int, copy: bool = True) -> HostMesh:
+        coords = np.ascontiguousarray(coords, dtype=np.int32).reshape(-1, 3)
+        h = _lib.MeshHost()
+        self._check(self._lib.vxp_terrain_mesh_host(self._h, coords.ctypes.data, coords.shape[0],
+                                                    seed & (2**64 - 1), mode, C.byref(h)))
+        return self._host_result(h, coords.shape[0], copy)
+
+    def terrain_fill_host(self, coords: np.ndarray, seed: int) -> np.ndarray:
+        coords = np.ascontiguousarray(coords, dtype=np.int32).reshape(-1, 3)
+        out = np.empty((coords.shape[0], CHUNK_VOXELS), dtype=np.uint16)
+        self._check(self._lib.vxp_terrain_fill_host(self._h, coords.ctypes.data, coords.shape[0],
+                                                    seed & (2**64 - 1), out.ctypes.data))
+        return out
