@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the chunk-meshing hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A step = one pass of the mesher over one batch of 4096 chunks (64 KiB each, 256 MiB per
+batch).  Four distinct batches (seeds 42..45, 1 GiB in total, > 126 MB of L2) rotate so no
+step re-reads what the previous one left in L2.  Prints ONE JSON line (rank 0).
+
+workloads (BASELINE.json configs):
+  terrain_culled   configs[1]  4096 noise-terrain chunks [0,16)^3, culled faces   (default)
+  terrain_greedy   configs[2]  same batches, greedy quads
+  checker_culled / checker_greedy   configs[3]  world-parity checkerboard, 98 304 quads per chunk
+  world_fused      configs[4]  65^3 = 274 625 chunk coords, fused terrain+greedy, sharded (strong scaling)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CHUNKS = 4096
+N_BATCHES = 4
+CHUNK_BYTES = 65536
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
+
+
+# --------------------------------------------------------------------------- helpers
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.t = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float, window: str):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "window": "nvidia-smi unavailable"}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 9]
+        if not rows:
+            rows, window = [r for (_, r) in self.rows if len(r) >= 9], "whole run (timed region shorter than one sample)"
+        busy = [r for r in rows if r[4].isdigit() and int(r[4]) > 0] or rows
+        sm = [float(r[1]) for r in busy if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in busy if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[5 + k].lower().startswith("active") for r in busy)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(busy), "window": window}
+
+
+def workload_coords(workload: str, rank: int, world: int):
+    from voxelphile_b200 import grid_coords
+    if workload == "world_fused":
+        return grid_coords((-32, -32, -32), (33, 33, 33))
+    return grid_coords((0, 0, 0), (16, 16, 16))
+
+
+def algorithmic_bytes(counts: np.ndarray) -> int:
+    """SPEC §8: read every voxel once, write 56 B per quad and the 8-byte meta entry."""
+    return int(counts.shape[0]) * (CHUNK_BYTES + 8) + 56 * int(counts.sum())
+
+
+# --------------------------------------------------------------------------- reference arm (CPU oracle)
+def run_reference(args):
+    """The reference has no implementation of this path; the comparand is the
+    in-repo CPU oracle (kind "port"), all host threads, on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from voxelphile_b200 import neighbour_table
+    mode = 1 if args.workload.endswith("greedy") or args.workload == "world_fused" else 0
+    threads = O.max_threads()
+    coords = workload_coords("terrain_culled", 0, 1)
+    nbr = neighbour_table(coords)
+    if args.workload.startswith("checker"):
+        vox = np.stack([O.pattern_fill(0, *map(int, c)) for c in coords[:256]])
+        nbr_s = neighbour_table(coords[:256])
+        sample = "256 checkerboard chunks (z-layer 0 of the 16^3 block) per step"
+        batches = [(vox, nbr_s)]
+    else:
+        batches = [(O.terrain_fill_batch(42 + k, coords, threads), nbr) for k in range(2)]
+        sample = "the full 4096-chunk batch per step (seeds 42,43 alternating)"
+    cap = int(max(O.mesh_batch_hash(v, n, mode, threads)[1].sum() for v, n in batches))
+    times = []
+    for s in range(args.warmup + args.steps):
+        v, n = batches[s % len(batches)]
+        t0 = time.perf_counter()
+        O.mesh_batch(v, n, mode, threads, capacity=cap)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    per_step = sum(times) / len(times)
+    value = batches[0][0].shape[0] / per_step
+    line = {
+        "impl": "reference", "metric": "chunks meshed/sec", "value": value, "unit": "chunks/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": args.workload, "chunks_per_step": int(batches[0][0].shape[0]),
+                   "note": "reference snapshot has no mesher; this is the in-repo CPU oracle (SPEC v1)"},
+        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="terrain_culled",
+                    choices=["terrain_culled", "terrain_greedy", "checker_culled", "checker_greedy", "world_fused"])
+    ap.add_argument("--impl", default="vxp", choices=["vxp", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from voxelphile_b200 import CULLED, GREEDY, PATTERN_CHECKER, Mesher, neighbour_table
+    from voxelphile_b200.shard import gather_counts, partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    m = Mesher(local)
+    m.use_current_torch_stream()
+    mode = GREEDY if args.workload.endswith("greedy") or args.workload == "world_fused" else CULLED
+    fused = args.workload == "world_fused"
+    coords_np = workload_coords(args.workload, rank, world)
+
+    # ---------------- inputs resident in HBM
+    if fused:
+        lo, hi = partition(coords_np.shape[0], rank, world)       # strong scaling: shard the world
+        my_coords = torch.from_numpy(np.ascontiguousarray(coords_np[lo:hi])).to(dev)
+        n_step = hi - lo
+        batches = [None]
+        scaling = "strong"
+    else:
+        nbr_np = neighbour_table(coords_np)
+        dcoords = torch.from_numpy(coords_np).to(dev)
+        dnbr = torch.from_numpy(nbr_np).to(dev)
+        n_step = N_CHUNKS
+        batches = []
+        for k in range(N_BATCHES):
+            if args.workload.startswith("checker"):
+                shift = torch.tensor([[16 * k, 0, 0]], dtype=torch.int32, device=dev)
+                batches.append(m.pattern_fill((dcoords + shift).contiguous(), PATTERN_CHECKER))
+            else:
+                batches.append(m.terrain_fill(dcoords, 42 + N_BATCHES * rank + k))   # weak scaling: own seeds per rank
+        scaling = "weak"
+    torch.cuda.synchronize()
+
+    def launch(k, out):
+        if fused:
+            return m.terrain_mesh(my_coords, 42, mode, out=out)
+        return m.mesh(batches[k % len(batches)], dnbr, mode, out=out)
+
+    # ---------------- size the output arena with one untimed pass per batch
+    probe = m.alloc_mesh(n_step, 0)
+    totals, counts = [], []
+    for k in range(len(batches)):
+        launch(k, probe)
+        torch.cuda.synchronize()
+        totals.append(int(probe.total.item()))
+        counts.append(probe.meta[:, 1].cpu().numpy().astype(np.int64))
+    out = m.alloc_mesh(n_step, max(totals) + 1)
+    alg_bytes = [algorithmic_bytes(c) if not fused else 12 * n_step + 56 * int(c.sum()) + 8 * n_step for c in counts]
+
+    # ---------------- warm-up (>= W steps and >= 0.3 s so clocks have ramped)
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_w = time.time()
+    k = 0
+    while k < args.warmup or time.time() - t_w < 0.3:
+        launch(k, out)
+        k += 1
+        if k % 64 == 0:
+            torch.cuda.synchronize()
+    barrier()
+
+    # ---------------- timed region: exactly K steps, per-launch events on the launching stream
+    launches0 = m.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e_start.record()
+    for s in range(args.steps):
+        ev[s][0].record()
+        launch(s, out)
+        ev[s][1].record()
+    # the one collective of the path: final host gather of mesh sizes (per-chunk quad counts)
+    final_counts = gather_counts(out.meta[:, 1].to(torch.int64), n_step * world, rank, world) if not fused else \
+        gather_counts(out.meta[:, 1].to(torch.int64), coords_np.shape[0], rank, world)
+    e_end.record()
+    barrier()
+    t1 = time.time()
+    launches = m.launches - launches0
+    elapsed_ms = torch.tensor([e_start.elapsed_time(e_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    ms_per_step = elapsed_ms / args.steps
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    clocks = sampler.stop(t0, t1, "timed region")
+    units_per_step = n_step * world if not fused else coords_np.shape[0]
+    value = units_per_step / (ms_per_step * 1e-3)
+
+    # roofline of the dominant (only) kernel: algorithmic bytes / mean launch duration
+    per_batch = {}
+    for s, t in enumerate(kernel_ms):
+        per_batch.setdefault(s % len(batches), []).append(t)
+    mean_ms = statistics.mean(kernel_ms)
+    mean_bytes = statistics.mean(alg_bytes[s % len(batches)] for s in range(args.steps))
+    peak, peak_src = hbm_peak()
+    achieved = mean_bytes / (mean_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "mesh_kernel" if not fused else "terrain_mesh_kernel",
+                "kernel_ms_mean": mean_ms, "kernel_ms_min": min(kernel_ms),
+                "algorithmic_bytes_per_launch": mean_bytes,
+                "note": "event bracket = 8-byte counter memset + kernel"}
+
+    # ---------------- e2e: host buffers in, host mesh out, through vxp_mesh_chunks_host / vxp_terrain_mesh_host
+    e2e = None
+    if args.e2e_steps > 0:
+        import ctypes as C
+        lib = m._lib
+        if fused:
+            h_coords = np.ascontiguousarray(coords_np[lo:hi])
+            call = lambda s: m.terrain_mesh_host(h_coords, 42, mode, copy=False)
+            h2d = h_coords.nbytes
+        else:
+            pinned = []
+            for b in batches[:2]:                       # two pinned 256 MiB host batches alternate
+                p = C.c_void_p()
+                assert lib.vxp_host_alloc(n_step * CHUNK_BYTES, C.byref(p)) == 0
+                torch.cuda.synchronize()
+                hb = np.frombuffer((C.c_char * (n_step * CHUNK_BYTES)).from_address(p.value), dtype=np.uint16)
+                hb[:] = b.cpu().numpy().view(np.uint16).reshape(-1)
+                pinned.append(p)
+            h_nbr = np.ascontiguousarray(nbr_np)
+            call = lambda s: m.mesh_host_ptr(pinned[s % 2].value, h_nbr.ctypes.data, n_step, mode)
+            h2d = n_step * CHUNK_BYTES + h_nbr.nbytes
+        m.use_stream(None)
+        for s in range(2):
+            res = call(s)
+        barrier()
+        tw0 = time.perf_counter()
+        d2h = 0
+        for s in range(args.e2e_steps):
+            res = call(s)
+            d2h += 8 + 8 * n_step + 56 * res.total_quads
+        barrier()
+        dt = torch.tensor([time.perf_counter() - tw0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": units_per_step * args.e2e_steps / float(dt.item()), "unit": "chunks/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h // args.e2e_steps),
+               "steps": args.e2e_steps, "api": "vxp_terrain_mesh_host" if fused else "vxp_mesh_chunks_host"}
+        m.use_current_torch_stream()
+        if not fused:
+            for p in pinned:
+                lib.vxp_host_free(p)
+
+    # ---------------- secondary measurements (not the headline; same hygiene, fewer steps)
+    also = {}
+    if not args.no_also and not fused and world == 1:
+        def timed(fn, steps=60):
+            for s in range(5):
+                fn(s)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for s in range(steps):
+                fn(s)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / steps
+
+        other = GREEDY if mode == CULLED else CULLED
+        oprobe = m.alloc_mesh(n_step, 0)
+        ocounts = []
+        for k in range(len(batches)):
+            m.mesh(batches[k], dnbr, other, out=oprobe)
+            torch.cuda.synchronize()
+            ocounts.append(oprobe.meta[:, 1].cpu().numpy().astype(np.int64))
+        oout = m.alloc_mesh(n_step, max(int(c.sum()) for c in ocounts) + 1)
+        ms = timed(lambda s: m.mesh(batches[s % len(batches)], dnbr, other, out=oout))
+        ob = statistics.mean(algorithmic_bytes(c) for c in ocounts)
+        also["greedy" if other == GREEDY else "culled"] = {
+            "chunks_per_s": n_step / (ms * 1e-3), "ms_per_step": ms, "hbm_gbs": ob / (ms * 1e-3) / 1e9,
+            "frac": ob / (ms * 1e-3) / 1e9 / peak, "quads_per_batch": float(np.mean([c.sum() for c in ocounts]))}
+        if not args.workload.startswith("checker"):
+            scratch = torch.empty_like(batches[0])
+            ms = timed(lambda s: m.terrain_fill(dcoords, 100 + s, out=scratch))
+            also["terrain_fill"] = {"chunks_per_s": n_step / (ms * 1e-3), "ms_per_step": ms,
+                                    "hbm_gbs": n_step * CHUNK_BYTES / (ms * 1e-3) / 1e9,
+                                    "frac": n_step * CHUNK_BYTES / (ms * 1e-3) / 1e9 / peak}
+            fprobe = m.alloc_mesh(n_step, 0)
+            m.terrain_mesh(dcoords, 42, GREEDY, out=fprobe)
+            torch.cuda.synchronize()
+            fout = m.alloc_mesh(n_step, int(fprobe.total.item()) + 1)
+            ms = timed(lambda s: m.terrain_mesh(dcoords, 42, GREEDY, out=fout))
+            also["fused_terrain_greedy"] = {"chunks_per_s": n_step / (ms * 1e-3), "ms_per_step": ms,
+                                            "quads": int(fprobe.total.item())}
+
+    # ---------------- CPU baseline: the oracle on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not fused:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        threads = O.max_threads()
+        n_cpu = N_CHUNKS if not args.workload.startswith("checker") else 256
+        hv = batches[0][:n_cpu].cpu().numpy().view(np.uint16)
+        hn = nbr_np[:n_cpu].copy()
+        hn[hn >= n_cpu] = -1
+        cap = int(O.mesh_batch_hash(hv, hn, mode, threads)[1].sum())
+        best = None
+        t_begin = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t_begin < 10 and reps < 20):
+            tc = time.perf_counter()
+            O.mesh_batch(hv, hn, mode, threads, capacity=cap)
+            dtc = time.perf_counter() - tc
+            best = dtc if best is None else min(best, dtc)
+            reps += 1
+        cpu = {"value": n_cpu / best, "unit": "chunks/s", "cores": threads, "kind": "port",
+               "sample": f"first {n_cpu} chunks of batch 0 (seed 42), best of {reps} passes, "
+                         f"in-repo C oracle (scalar, pthreads); the reference has no mesher to time"}
+
+    if rank == 0:
+        line = {
+            "metric": "chunks meshed/sec", "value": value, "unit": "chunks/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": args.workload, "chunks_per_step_per_gpu": n_step, "chunk": "32^3 u16",
+                       "mode": "greedy" if mode == GREEDY else "culled",
+                       "batches": f"{len(batches)} rotating batches of {n_step} chunks "
+                                  f"({len(batches) * n_step * CHUNK_BYTES >> 20} MiB > 126 MB L2)" if not fused else
+                                  "fused terrain+mesh, no stored voxels",
+                       "quads_per_step_per_gpu": float(np.mean([c.sum() for c in counts])),
+                       "voxels_per_s": value * 32768, "spec": "SPEC.md v1 (builder-defined; parity unpinned)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "gathered_quads": int(final_counts.sum().item()), "also": also,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    m.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -96,9 +96,12 @@ vxp_status vxp_terrain_fill_batch(vxp_ctx *ctx, const vxp_coord *d_coords, uint3
 /* SPEC §7 test patterns. */
 vxp_status vxp_pattern_fill_batch(vxp_ctx *ctx, const vxp_coord *d_coords, uint32_t n,
                                   vxp_pattern pattern, uint16_t *d_voxels);
-/* SPEC §2-§5: mesh n stored chunks.  d_nbr6 may be NULL (all sides air).
- * Overflow of out->capacity_quads is only visible in *out->total_quads and
- * meta[i].first_quad == 0xFFFFFFFF (the call itself is asynchronous). */
+/* SPEC §2-§5: mesh the first n chunks stored at d_voxels.  d_nbr6 (n x 6) may be
+ * NULL (all sides air); its entries may name any chunk stored at d_voxels,
+ * including read-only "halo" chunks at index >= n that are not meshed
+ * themselves (multi-GPU seam layers).  Overflow of out->capacity_quads is only
+ * visible in *out->total_quads and meta[i].first_quad == 0xFFFFFFFF (the call
+ * itself is asynchronous). */
 vxp_status vxp_mesh_batch(vxp_ctx *ctx, const uint16_t *d_voxels, const int32_t *d_nbr6,
                           uint32_t n, vxp_mode mode, const vxp_mesh_dev *out);
 /* Terrain + mesh without materialising voxels: chunk d_coords[i] is meshed
@@ -109,8 +112,10 @@ vxp_status vxp_terrain_mesh_fused(vxp_ctx *ctx, const vxp_coord *d_coords, uint3
 /* ---- host level: host pointers in, context-owned pinned results out ---- */
 vxp_status vxp_terrain_fill_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
                                  uint64_t seed, uint16_t *voxels);
+/* voxels holds n_stored >= n chunks; the first n are meshed, nbr6 (n x 6) indexes
+ * all n_stored of them. */
 vxp_status vxp_mesh_chunks_host(vxp_ctx *ctx, const uint16_t *voxels, const int32_t *nbr6,
-                                uint32_t n, vxp_mode mode, vxp_mesh_host *out);
+                                uint32_t n, uint32_t n_stored, vxp_mode mode, vxp_mesh_host *out);
 vxp_status vxp_terrain_mesh_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
                                  uint64_t seed, vxp_mode mode, vxp_mesh_host *out);
 

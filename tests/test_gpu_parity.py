@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libvxp.so), against the CPU
+oracle and the golden fixtures.  Bit-exact: canonical keys AND the vertex/index bytes
+re-ordered by key (SPEC §5).  Comparand = in-repo oracle, SPEC v1 (parity with the
+reference itself is unpinned — SURVEY.md §0)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import spec_py as S
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "spec_v1.npz")
+MODES = [(0, "culled"), (1, "greedy")]
+
+
+@pytest.fixture(scope="module")
+def G():
+    return np.load(GOLDEN)
+
+
+@pytest.fixture(scope="module")
+def mesher():
+    import torch
+    from voxelphile_b200 import Mesher
+    assert torch.cuda.is_available()
+    m = Mesher(0)
+    m.use_current_torch_stream()
+    yield m
+    m.close()
+
+
+def dev(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.view(dtype)
+    return t.cuda()
+
+
+def gpu_mesh(mesher, vox, nbr, mode, capacity=None, n_mesh=None):
+    """Mesh on the GPU through vxp_mesh_batch; returns a HostMesh."""
+    import torch
+    vox = np.ascontiguousarray(vox, dtype=np.uint16).reshape(-1, 32768)
+    dv = dev(vox.view(np.int16))
+    dn = dev(np.asarray(nbr, dtype=np.int32)) if nbr is not None else None
+    cap = capacity if capacity is not None else vox.shape[0] * 98304
+    out = mesher.mesh(dv, dn, mode, capacity=cap, n_mesh=n_mesh)
+    torch.cuda.synchronize()
+    return out.to_host()
+
+
+def check_against_oracle(host, vox, nbr, mode, expect_keys=None):
+    """Every chunk: sorted keys equal, and vertex/index bytes equal the oracle's expansion."""
+    n = vox.shape[0]
+    assert host.meta.shape == (n, 2)
+    total = 0
+    used = np.zeros(host.total_quads, dtype=bool)
+    for i in range(n):
+        first, cnt = int(host.meta[i, 0]), int(host.meta[i, 1])
+        nbs = [None if (nbr is None or nbr[i, f] < 0) else vox[nbr[i, f]] for f in range(6)]
+        want = O.mesh_chunk_keys(vox[i], nbs, mode) if expect_keys is None else expect_keys[i]
+        assert cnt == len(want), (i, cnt, len(want))
+        total += cnt
+        if cnt == 0:
+            continue
+        assert first + cnt <= host.total_quads
+        assert not used[first:first + cnt].any(), "chunk ranges overlap"
+        used[first:first + cnt] = True
+        v, ix = host.chunk(i)
+        got = S.keys_from_verts(v)
+        order = np.argsort(got, kind="stable")
+        assert np.array_equal(got[order], want), f"chunk {i}: key sets differ"
+        # vertex bytes: expand the oracle's quads and compare in key order
+        ref_v = np.empty((cnt, 4), dtype=np.uint64)
+        step = max(1, cnt // 512)          # full check on small meshes, strided sample on huge ones
+        for q in range(0, cnt, step):
+            ref_v[q], _ = O.expand_quad(int(want[q]), 0)
+            assert np.array_equal(v[order[q]], ref_v[q]), (i, q)
+        # every vertex of every quad carries the same (f, id, w, h) and corner numbers 0..3
+        w0 = (v & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        assert np.array_equal((w0 >> 21) & 3, np.tile(np.arange(4), (cnt, 1)))
+        assert (v >> np.uint64(32) == (v[:, :1] >> np.uint64(32))).all()
+        assert (((w0 >> 18) & 7) == ((w0[:, :1] >> 18) & 7)).all()
+        # indices are chunk-local ordinals
+        want_ix = 4 * np.arange(cnt, dtype=np.uint32)[:, None] + np.array([0, 1, 2, 2, 3, 0], dtype=np.uint32)
+        assert np.array_equal(ix, want_ix), f"chunk {i}: indices"
+    assert total == host.total_quads and used.all()
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_golden_cases(G, mesher, mode, mname):
+    for name in [str(x) for x in G["case_names"]]:
+        vox, nbr = G[f"{name}/vox"], G[f"{name}/nbr"]
+        keys, offs = G[f"{name}/{mname}/keys"], G[f"{name}/{mname}/offs"]
+        expect = [keys[offs[i]:offs[i + 1]] for i in range(vox.shape[0])]
+        host = gpu_mesh(mesher, vox, nbr, mode)
+        check_against_oracle(host, vox, nbr, mode, expect_keys=expect)
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+@pytest.mark.parametrize("p", [0.01, 0.1, 0.5, 0.9, 0.99])
+def test_differential_random(mesher, mode, mname, p):
+    rng = np.random.default_rng(int(p * 1000) + mode)
+    n = 24
+    vox = np.where(rng.random((n, 32768)) < p, rng.integers(1, 5, (n, 32768)), 0).astype(np.uint16)
+    nbr = rng.integers(-1, n, size=(n, 6)).astype(np.int32)     # arbitrary, asymmetric neighbour links
+    host = gpu_mesh(mesher, vox, nbr, mode)
+    check_against_oracle(host, vox, nbr, mode)
+
+
+def test_many_ids_and_long_runs(mesher):
+    """Ids up to 0xFFFF, stripes and plateaus that stress width/height extension."""
+    rng = np.random.default_rng(11)
+    n = 8
+    v = np.zeros((n, 32, 32, 32), dtype=np.uint16)
+    v[0] = 0xFFFF
+    v[1, :, :16, :] = 0x8000; v[1, :, 16:, :] = 0x7FFF
+    v[2] = rng.integers(1, 3, (32, 1, 1))            # id varies along z only
+    v[3] = rng.integers(1, 3, (1, 32, 1))            # along y only
+    v[4] = rng.integers(1, 3, (1, 1, 32))            # along x only
+    v[5, ::2] = 1                                    # alternating solid/air layers
+    v[6, :, ::2] = 2
+    v[7, :, :, ::2] = 3
+    vox = v.reshape(n, -1)
+    for mode, _ in MODES:
+        host = gpu_mesh(mesher, vox, None, mode)
+        check_against_oracle(host, vox, None, mode)
+
+
+def test_terrain_fill_bit_exact(G, mesher):
+    import torch
+    from voxelphile_b200 import grid_coords
+    seed = int(G["terrain_seed"][0])
+    got = mesher.terrain_fill(dev(G["terrain_coords"]), seed)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy().view(np.uint16), G["terrain_vox"])
+    for seed, lo in ((42, (0, 6, 0)), (1, (-3, 5, -2)), (2**63 + 12345, (100, 7, -100))):
+        coords = grid_coords(lo, (lo[0] + 3, lo[1] + 5, lo[2] + 3))
+        got = mesher.terrain_fill(dev(coords), seed)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy().view(np.uint16), O.terrain_fill_batch(seed, coords))
+
+
+def test_pattern_fill_bit_exact(mesher):
+    import torch
+    from voxelphile_b200 import grid_coords
+    coords = grid_coords((-1, -1, -1), (1, 1, 1))
+    for pid in (0, 1):
+        got = mesher.pattern_fill(dev(coords), pid)
+        torch.cuda.synchronize()
+        want = np.stack([O.pattern_fill(pid, *map(int, c)) for c in coords])
+        assert np.array_equal(got.cpu().numpy().view(np.uint16), want)
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_terrain_block_stored_path(mesher, mode, mname):
+    """Config 1/2/3 in miniature: a block of seed-42 terrain chunks with real neighbours."""
+    import torch
+    from voxelphile_b200 import grid_coords, neighbour_table
+    coords = grid_coords((0, 5, 0), (4, 11, 4))
+    nbr = neighbour_table(coords)
+    dvox = mesher.terrain_fill(dev(coords), 42)
+    out = mesher.mesh(dvox, dev(nbr), mode, capacity=coords.shape[0] * 4096)
+    torch.cuda.synchronize()
+    vox = dvox.cpu().numpy().view(np.uint16)
+    check_against_oracle(out.to_host(), vox, nbr, mode)
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_fused_terrain_mesh(mesher, mode, mname):
+    """Fused path: neighbours are the infinite terrain itself."""
+    import torch
+    from voxelphile_b200 import grid_coords
+    seed = 42
+    coords = np.concatenate([grid_coords((0, 6, 0), (3, 10, 2)), np.array([[-7, 8, 3], [5, 0, 5], [5, 30, 5]], np.int32)])
+    out = mesher.terrain_mesh(dev(coords), seed, mode, capacity=coords.shape[0] * 8192)
+    torch.cuda.synchronize()
+    host = out.to_host()
+    expect = []
+    for c in coords:
+        c = tuple(map(int, c))
+        vox = O.terrain_fill(seed, *c)
+        nbs = [O.terrain_fill(seed, c[0] + d[0], c[1] + d[1], c[2] + d[2]) for d in S.DIRS]
+        expect.append((vox, nbs))
+    for i, (vox, nbs) in enumerate(expect):
+        first, cnt = int(host.meta[i, 0]), int(host.meta[i, 1])
+        want = O.mesh_chunk_keys(vox, nbs, mode)
+        assert cnt == len(want), (i, cnt, len(want))
+        v, ix = host.chunk(i)
+        assert np.array_equal(np.sort(S.keys_from_verts(v)), want), i
+    assert host.total_quads == int(host.meta[:, 1].sum())
+
+
+def test_checkerboard_worst_case_property(mesher):
+    """Config 4 at reduced count: every chunk of a world-parity checkerboard block emits exactly
+    98 304 quads in both modes (interior chunks see the pattern continue across all seams)."""
+    import torch
+    from voxelphile_b200 import grid_coords, neighbour_table, PATTERN_CHECKER
+    coords = grid_coords((0, 0, 0), (3, 3, 3))
+    nbr = neighbour_table(coords)
+    dvox = mesher.pattern_fill(dev(coords), PATTERN_CHECKER)
+    for mode, _ in MODES:
+        out = mesher.mesh(dvox, dev(nbr), mode, capacity=27 * 98304)
+        torch.cuda.synchronize()
+        host = out.to_host()
+        assert (host.meta[:, 1] == 98304).all() and host.total_quads == 27 * 98304
+        keys = S.keys_from_verts(host.chunk(13)[0])                  # the interior chunk
+        assert len(np.unique(keys)) == 98304
+        assert ((keys >> np.uint64(21)) & np.uint64(1023) == 0).all()   # all 1x1
+        vox = dvox.cpu().numpy().view(np.uint16)
+        nbs = [vox[nbr[13, f]] for f in range(6)]
+        assert np.array_equal(np.sort(keys), O.mesh_chunk_keys(vox[13], nbs, mode))
+
+
+def test_capacity_overflow_contract(G, mesher):
+    vox, nbr = G["terrain42/vox"], G["terrain42/nbr"]
+    need = int(G["terrain42/greedy/offs"][-1])
+    import torch
+    from voxelphile_b200 import MeshError
+    out = mesher.mesh(dev(vox.view(np.int16)), dev(nbr), 1, capacity=need // 3)
+    torch.cuda.synchronize()
+    assert int(out.total.item()) == need
+    meta = out.meta.cpu().numpy().view(np.uint32)
+    lost = meta[:, 0] == 0xFFFFFFFF
+    assert lost.any() and not lost.all()
+    counts = np.diff(G["terrain42/greedy/offs"])
+    assert np.array_equal(meta[:, 1], counts)
+    with pytest.raises(MeshError) as e:
+        out.to_host()
+    assert e.value.kind == "Capacity"
+    # exact capacity fits
+    out = mesher.mesh(dev(vox.view(np.int16)), dev(nbr), 1, capacity=need)
+    torch.cuda.synchronize()
+    check_against_oracle(out.to_host(), vox, nbr, 1)
+
+
+def test_host_level_api(G, mesher):
+    """vxp_mesh_chunks_host / vxp_terrain_mesh_host / vxp_terrain_fill_host: host buffers in and out,
+    including the internal arena growth (random_p50 needs more than the first-guess capacity)."""
+    for name in ("terrain42", "random_p50", "empty"):
+        vox, nbr = G[f"{name}/vox"], G[f"{name}/nbr"]
+        for mode, _ in MODES:
+            host = mesher.mesh_host(vox, nbr, mode)
+            check_against_oracle(host, vox, nbr, mode)
+    coords = G["terrain_coords"]
+    assert np.array_equal(mesher.terrain_fill_host(coords, 42), G["terrain_vox"])
+    host = mesher.terrain_mesh_host(np.array([[0, 8, 0]], np.int32), 42, 1)
+    vox = O.terrain_fill(42, 0, 8, 0)
+    nbs = [O.terrain_fill(42, d[0], 8 + d[1], d[2]) for d in S.DIRS]
+    assert np.array_equal(np.sort(S.keys_from_verts(host.chunk(0)[0])), O.mesh_chunk_keys(vox, nbs, 1))
+    empty = mesher.mesh_host(np.zeros((0, 32768), np.uint16), None, 1)
+    assert empty.total_quads == 0 and empty.meta.shape == (0, 2)
+
+
+def test_bad_arguments(mesher):
+    from voxelphile_b200 import MeshError
+    vox = np.zeros((2, 32768), np.uint16)
+    with pytest.raises(MeshError) as e:
+        mesher.mesh_host(vox, np.array([[5, -1, -1, -1, -1, -1], [-1] * 6], np.int32), 1)
+    assert e.value.kind == "BadArg"
+    with pytest.raises(MeshError):
+        mesher.mesh_host(vox, None, 7)
+
+
+def test_sharded_union_equals_single(mesher):
+    """Multi-GPU semantics on one device: meshing two shards (each with the one-chunk seam layer
+    duplicated read-only) yields the same per-chunk canonical meshes as meshing the whole batch."""
+    import torch
+    from voxelphile_b200 import grid_coords, neighbour_table
+    from voxelphile_b200.shard import shard_with_halo
+    coords = grid_coords((0, 6, 0), (4, 10, 4))
+    nbr = neighbour_table(coords)
+    dvox = mesher.terrain_fill(dev(coords), 42)
+    torch.cuda.synchronize()
+    vox = dvox.cpu().numpy().view(np.uint16)
+    whole = gpu_mesh(mesher, vox, nbr, 1, capacity=len(coords) * 4096)
+    for world in (2, 3):
+        seen = 0
+        for rank in range(world):
+            sh = shard_with_halo(coords, rank, world)
+            part = gpu_mesh(mesher, vox[sh.batch_index], sh.nbr6, 1, capacity=len(sh.batch_index) * 4096,
+                            n_mesh=sh.n_owned)
+            for local, g in enumerate(sh.batch_index[:sh.n_owned]):
+                a = np.sort(S.keys_from_verts(part.chunk(local)[0]))
+                b = np.sort(S.keys_from_verts(whole.chunk(int(g))[0]))
+                assert np.array_equal(a, b), (world, rank, int(g))
+                seen += 1
+        assert seen == len(coords)

@@ -54,7 +54,8 @@ SIGNATURES = {
     "vxp_mesh_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(MeshDev)]),
     "vxp_terrain_mesh_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(MeshDev)]),
     "vxp_terrain_fill_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]),
-    "vxp_mesh_chunks_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(MeshHost)]),
+    "vxp_mesh_chunks_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                             C.POINTER(MeshHost)]),
     "vxp_terrain_mesh_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(MeshHost)]),
 }
 

@@ -345,17 +345,17 @@ vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
 }
 
 vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int32_t* nbr6, uint32_t n,
-                                vxp_mode mode, vxp_mesh_host* out) {
-    if (!ctx || !out || !valid_mode(mode) || (n && !voxels)) return VXP_ERR_BAD_ARG;
+                                uint32_t n_stored, vxp_mode mode, vxp_mesh_host* out) {
+    if (!ctx || !out || !valid_mode(mode) || n_stored < n || (n && !voxels)) return VXP_ERR_BAD_ARG;
     if (nbr6)
         for (size_t i = 0; i < (size_t)n * 6; ++i)
-            if (nbr6[i] < -1 || nbr6[i] >= (int64_t)n) return VXP_ERR_BAD_ARG;
+            if (nbr6[i] < -1 || nbr6[i] >= (int64_t)n_stored) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     vxp_status s;
-    if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
+    if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n_stored, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_nbr6, &ctx->nbr_cap, n, 6)) != VXP_OK) return s;
     if (n) {
-        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels, voxels, (size_t)n * VXP_CHUNK_VOXELS * sizeof(uint16_t),
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels, voxels, (size_t)n_stored * VXP_CHUNK_VOXELS * sizeof(uint16_t),
                                       cudaMemcpyHostToDevice, ctx->stream));
         if (nbr6)
             VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t),

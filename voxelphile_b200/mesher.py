@@ -180,9 +180,11 @@ class Mesher:
         return out
 
     def mesh(self, voxels: "torch.Tensor", nbr6: Optional["torch.Tensor"], mode: int,
-             out: Optional[DeviceMesh] = None, capacity: Optional[int] = None) -> DeviceMesh:
-        """voxels: 16-bit [n,32768] device tensor; nbr6: int32 [n,6] or None. Asynchronous."""
-        n = voxels.shape[0]
+             out: Optional[DeviceMesh] = None, capacity: Optional[int] = None,
+             n_mesh: Optional[int] = None) -> DeviceMesh:
+        """voxels: 16-bit [n_stored,32768] device tensor; nbr6: int32 [n,6] or None. Asynchronous.
+        Only the first ``n_mesh`` (default all) chunks are meshed; the rest are read-only halo chunks."""
+        n = voxels.shape[0] if n_mesh is None else n_mesh
         assert voxels.is_cuda and voxels.is_contiguous() and voxels.element_size() == 2
         if nbr6 is not None:
             assert nbr6.is_cuda and nbr6.is_contiguous() and nbr6.shape == (n, 6)
@@ -217,22 +219,29 @@ class Mesher:
         return HostMesh(view(h.verts, 4 * q, np.uint64), view(h.indices, 6 * q, np.uint32),
                         view(h.meta, 2 * n, np.uint32).reshape(n, 2), q)
 
-    def mesh_host(self, voxels: np.ndarray, nbr6: Optional[np.ndarray], mode: int, copy: bool = True) -> HostMesh:
-        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call)."""
+    def mesh_host(self, voxels: np.ndarray, nbr6: Optional[np.ndarray], mode: int, copy: bool = True,
+                  n_mesh: Optional[int] = None) -> HostMesh:
+        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call).
+
+        ``n_mesh`` < len(voxels) marks the trailing chunks as read-only halo chunks."""
         voxels = np.ascontiguousarray(voxels, dtype=np.uint16).reshape(-1, CHUNK_VOXELS)
-        n = voxels.shape[0]
+        n_stored = voxels.shape[0]
+        n = n_stored if n_mesh is None else n_mesh
         nptr = None
         if nbr6 is not None:
             nbr6 = np.ascontiguousarray(nbr6, dtype=np.int32).reshape(n, 6)
             nptr = nbr6.ctypes.data
         h = _lib.MeshHost()
-        self._check(self._lib.vxp_mesh_chunks_host(self._h, voxels.ctypes.data, nptr, n, mode, C.byref(h)))
+        self._check(self._lib.vxp_mesh_chunks_host(self._h, voxels.ctypes.data, nptr, n, n_stored, mode,
+                                                   C.byref(h)))
         return self._host_result(h, n, copy)
 
-    def mesh_host_ptr(self, voxels_ptr: int, nbr6_ptr: Optional[int], n: int, mode: int) -> HostMesh:
+    def mesh_host_ptr(self, voxels_ptr: int, nbr6_ptr: Optional[int], n: int, mode: int,
+                      n_stored: Optional[int] = None) -> HostMesh:
         """Same, from raw (e.g. pinned) host pointers; the result aliases context-owned pinned memory."""
         h = _lib.MeshHost()
-        self._check(self._lib.vxp_mesh_chunks_host(self._h, voxels_ptr, nbr6_ptr, n, mode, C.byref(h)))
+        self._check(self._lib.vxp_mesh_chunks_host(self._h, voxels_ptr, nbr6_ptr, n,
+                                                   n if n_stored is None else n_stored, mode, C.byref(h)))
         return self._host_result(h, n, copy=False)
 
     def terrain_mesh_host(self, coords: np.ndarray, seed: int, mode: int, copy: bool = True) -> HostMesh:
