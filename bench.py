@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--impl", default="vxp", choices=["vxp", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--soak-seconds", type=float, default=0.3, help="minimum warm-up duration (0 under ncu)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -181,6 +183,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one explicit non-default stream for everything: torch allocations/fills, our kernels and the
+    # timing events all live on it (torch.cuda.Event only sees torch's current stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     m = Mesher(local)
     m.use_current_torch_stream()
     mode = GREEDY if args.workload.endswith("greedy") or args.workload == "world_fused" else CULLED
@@ -230,7 +236,7 @@ def main():
     sampler.start()
     t_w = time.time()
     k = 0
-    while k < args.warmup or time.time() - t_w < 0.3:
+    while k < args.warmup or time.time() - t_w < args.soak_seconds:
         launch(k, out)
         k += 1
         if k % 64 == 0:
@@ -364,7 +370,7 @@ def main():
 
     # ---------------- CPU baseline: the oracle on this box's host cores (rank 0, N=1 only)
     cpu = None
-    if rank == 0 and world == 1 and not fused:
+    if rank == 0 and world == 1 and not fused and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O
         threads = O.max_threads()

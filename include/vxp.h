@@ -71,9 +71,11 @@ typedef struct vxp_mesh_host {
 /* ---- context ----------------------------------------------------------- */
 vxp_status vxp_ctx_create(int device, vxp_ctx **out);
 void vxp_ctx_destroy(vxp_ctx *ctx);
-/* Run device-level calls on the caller's CUDA stream (a cudaStream_t); NULL
- * restores the context's own stream. */
+/* Run all of this context's work on the caller's CUDA stream (a cudaStream_t).
+ * NULL means what it means to CUDA: the legacy default stream.
+ * vxp_ctx_reset_stream returns to the context's own non-blocking stream. */
 vxp_status vxp_ctx_set_stream(vxp_ctx *ctx, void *cuda_stream);
+vxp_status vxp_ctx_reset_stream(vxp_ctx *ctx);
 vxp_status vxp_ctx_synchronize(vxp_ctx *ctx);
 const char *vxp_status_str(vxp_status s);
 /* Detail of the last VXP_ERR_CUDA on this context ("" if none). */

@@ -227,7 +227,13 @@ void vxp_ctx_destroy(vxp_ctx* ctx) {
 
 vxp_status vxp_ctx_set_stream(vxp_ctx* ctx, void* cuda_stream) {
     if (!ctx) return VXP_ERR_BAD_ARG;
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return VXP_OK;
+}
+
+vxp_status vxp_ctx_reset_stream(vxp_ctx* ctx) {
+    if (!ctx) return VXP_ERR_BAD_ARG;
+    ctx->stream = ctx->own_stream;
     return VXP_OK;
 }
 

@@ -129,7 +129,11 @@ class Mesher:
         return int(self._lib.vxp_launch_count(self._h))
 
     def use_stream(self, stream: Optional["torch.cuda.Stream"]):
-        self._check(self._lib.vxp_ctx_set_stream(self._h, stream.cuda_stream if stream is not None else None))
+        """Run on a torch stream; ``None`` returns to the context's own non-blocking stream."""
+        if stream is None:
+            self._check(self._lib.vxp_ctx_reset_stream(self._h))
+        else:
+            self._check(self._lib.vxp_ctx_set_stream(self._h, stream.cuda_stream or None))
 
     def use_current_torch_stream(self):
         import torch
