@@ -50,7 +50,8 @@ typedef enum vxp_pattern { VXP_PATTERN_CHECKER = 0, VXP_PATTERN_SOLID4 = 1 } vxp
 typedef struct vxp_coord { int32_t x, y, z; } vxp_coord;           /* chunk coordinate */
 typedef struct vxp_chunk_meta { uint32_t first_quad, quad_count; } vxp_chunk_meta;
 
-/* Batch mesh in DEVICE memory (SPEC §5).  All four arrays are caller-owned. */
+/* Batch mesh in DEVICE memory (SPEC §5).  All four arrays are caller-owned.
+ * verts must be 32-byte aligned (one quad = one 32-byte store), indices 8-byte aligned. */
 typedef struct vxp_mesh_dev {
     uint64_t *verts;          /* 4 * capacity_quads vertices, 8 B each        */
     uint32_t *indices;        /* 6 * capacity_quads indices                    */

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvxp.so")
+LIB_PATH = os.environ.get("VXP_LIB", os.path.join(_HERE, "libvxp.so"))  # VXP_LIB: profiling builds only
 
 VXP_OK, VXP_ERR_BAD_ARG, VXP_ERR_NO_DEVICE, VXP_ERR_OOM, VXP_ERR_CAPACITY, VXP_ERR_CUDA = range(6)
 MODE_CULLED, MODE_GREEDY = 0, 1

@@ -26,6 +26,9 @@ struct vxp_ctx {
     vxp_chunk_meta* d_meta = nullptr; size_t meta_cap = 0;   // chunks
     uint64_t* d_verts = nullptr;    uint32_t* d_indices = nullptr; size_t quads_cap = 0;
     uint64_t* d_total = nullptr;
+    // boundary-summary scratch of the mesh kernel (vxp_launch.h: BoundaryScratch)
+    uint32_t* d_tags = nullptr;     unsigned long long* d_planes = nullptr;  size_t bnd_cap = 0;   // chunks
+    uint32_t epoch = 0;
     vxp_chunk_meta* h_meta = nullptr; size_t h_meta_cap = 0;
     uint64_t* h_verts = nullptr;    uint32_t* h_indices = nullptr; size_t h_quads_cap = 0;
     uint64_t* h_total = nullptr;
@@ -108,13 +111,39 @@ vxp_status grow_host_quads(vxp_ctx* ctx, size_t need) {
     return VXP_OK;
 }
 
+// Scratch for one mesh launch over n chunks: grown on demand (cudaFree synchronises with any launch
+// still using the old area), tags zeroed on allocation and when the 30-bit epoch wraps.
+vxp_status next_boundary_scratch(vxp_ctx* ctx, uint32_t n, vxp::BoundaryScratch* out) {
+    if (n > ctx->bnd_cap) {
+        const size_t want = (size_t)n + n / 4;
+        if (ctx->d_tags) VXP_CUDA(ctx, cudaFree(ctx->d_tags));
+        if (ctx->d_planes) VXP_CUDA(ctx, cudaFree(ctx->d_planes));
+        ctx->d_tags = nullptr;
+        ctx->d_planes = nullptr;
+        ctx->bnd_cap = 0;
+        VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_tags), vxp::boundary_tag_bytes((uint32_t)want)));
+        VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_planes), vxp::boundary_plane_bytes((uint32_t)want)));
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_tags, 0, vxp::boundary_tag_bytes((uint32_t)want), ctx->stream));
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_planes, 0, vxp::boundary_plane_bytes((uint32_t)want), ctx->stream));
+        ctx->bnd_cap = want;
+        ctx->epoch = 0;
+    }
+    if (++ctx->epoch >= (1u << 30)) {
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_tags, 0, vxp::boundary_tag_bytes((uint32_t)ctx->bnd_cap), ctx->stream));
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_planes, 0, vxp::boundary_plane_bytes((uint32_t)ctx->bnd_cap), ctx->stream));
+        ctx->epoch = 1;
+    }
+    *out = vxp::BoundaryScratch{ctx->d_tags, ctx->d_planes, ctx->epoch};
+    return VXP_OK;
+}
+
 bool valid_mode(vxp_mode m) { return m == VXP_MODE_CULLED || m == VXP_MODE_GREEDY; }
 
 bool valid_out(const vxp_mesh_dev* o, uint32_t n) {
     if (!o || !o->total_quads) return false;
     if (n && !o->meta) return false;
     if (o->capacity_quads && (!o->verts || !o->indices)) return false;
-    if (!aligned16(o->verts) || (reinterpret_cast<uintptr_t>(o->indices) & 7u)) return false;
+    if ((reinterpret_cast<uintptr_t>(o->verts) & 31u) || (reinterpret_cast<uintptr_t>(o->indices) & 7u)) return false;
     if (o->capacity_quads > 0xFFFFFFFEull) return false;  // first_quad is a u32; 0xFFFFFFFF is the overflow mark
     return true;
 }
@@ -217,6 +246,8 @@ void vxp_ctx_destroy(vxp_ctx* ctx) {
     cudaFree(ctx->d_verts);
     cudaFree(ctx->d_indices);
     cudaFree(ctx->d_total);
+    cudaFree(ctx->d_tags);
+    cudaFree(ctx->d_planes);
     cudaFreeHost(ctx->h_meta);
     cudaFreeHost(ctx->h_verts);
     cudaFreeHost(ctx->h_indices);
@@ -316,7 +347,12 @@ vxp_status vxp_mesh_batch(vxp_ctx* ctx, const uint16_t* d_voxels, const int32_t*
     if (!ctx || !valid_mode(mode) || !valid_out(out, n)) return VXP_ERR_BAD_ARG;
     if (n && (!d_voxels || !aligned16(d_voxels))) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
-    VXP_CUDA(ctx, vxp::launch_mesh(d_voxels, d_nbr6, n, mode == VXP_MODE_GREEDY, *out, ctx->stream));
+    vxp::BoundaryScratch scratch{nullptr, nullptr, 0};
+    if (n) {
+        const vxp_status s = next_boundary_scratch(ctx, n, &scratch);
+        if (s != VXP_OK) return s;
+    }
+    VXP_CUDA(ctx, vxp::launch_mesh(d_voxels, d_nbr6, n, mode == VXP_MODE_GREEDY, *out, scratch, ctx->stream));
     ctx->launches += n ? 1 : 0;
     return VXP_OK;
 }
@@ -371,7 +407,9 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
     return mesh_into_host(
         ctx, n,
         [&](const vxp_mesh_dev& dev) {
-            return vxp::launch_mesh(ctx->d_voxels, d_nbr, n, mode == VXP_MODE_GREEDY, dev, ctx->stream);
+            vxp::BoundaryScratch scratch{nullptr, nullptr, 0};
+            if (n && next_boundary_scratch(ctx, n, &scratch) != VXP_OK) return cudaErrorMemoryAllocation;
+            return vxp::launch_mesh(ctx->d_voxels, d_nbr, n, mode == VXP_MODE_GREEDY, dev, scratch, ctx->stream);
         },
         out);
 }

@@ -2,8 +2,11 @@
 // fused terrain+mesh.  SPEC.md v1.  Host launchers at the bottom (C++ linkage, used by vxp_api.cu).
 #include <climits>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "vxp_launch.h"
-#include "vxp_mesh.cuh"
+#include "vxp_mesh4.cuh"
 
 namespace vxp {
 
@@ -84,54 +87,25 @@ __global__ void __launch_bounds__(kThreads) pattern_fill_kernel(const vxp_coord*
 }
 
 // ====================================================================== stored-chunk meshing
-// v1: one CTA per chunk, the tile staged by one bulk TMA; two CTAs per SM overlap load and compute.
-template <bool kGreedy>
-__global__ void __launch_bounds__(kThreads, 2)
-mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, MeshOut out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    MeshSmem& sm = *reinterpret_cast<MeshSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const uint32_t chunk = blockIdx.x;
-    if (chunk >= n) return;
-    const uint16_t* gvox = voxels + (size_t)chunk * VXP_CHUNK_VOXELS;
-
-    if (tid == 0) {
-        sm.ones = kFull;
-        mbar_init(&sm.mbar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(&sm.mbar, kTileBytes);
-        tma_load_1d(sm.tile.vox, gvox, kTileBytes, &sm.mbar);
-    }
-    load_halo(sm, voxels, nbr6, chunk);     // overlaps the TMA
-    __syncthreads();                        // barrier init visible to all waiters
-    mbar_wait(&sm.mbar, 0);
-
-    const bool uniform = build_occupancy(sm);   // contains a block barrier: occ + halos published
-    if (uniform && sm.tile.vox[0] == 0) {       // all air: no faces
-        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
-        return;
-    }
-    if (kGreedy && !uniform) build_equality(sm);
-    __syncthreads();                            // tile is dead from here on (aliased by ht/vt/staging)
-    build_masks<kGreedy>(sm, uniform);
-    __syncthreads();
-    emit_chunk<kGreedy>(sm, chunk, uniform, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); });
-}
+// v4::mesh_kernel lives in vxp_mesh4.cuh (one CTA per chunk, three CTAs per SM).
 
 // ====================================================================== fused terrain + mesh
-// The tile is generated in shared memory from the height field; voxels never reach HBM.
+// The tile is generated in shared memory from the height field; voxels never reach HBM and the
+// halo comes straight from the heights of the 34x34 column footprint.
 template <bool kGreedy>
-__global__ void __launch_bounds__(kThreads, 2)
-terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t seed, MeshOut out) {
+__global__ void __launch_bounds__(kThreads, 3)
+terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t seed, v4::MeshOut out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    MeshSmem& sm = *reinterpret_cast<MeshSmem*>(smem_raw);
-    __shared__ int s_h[34 * 34];   // heights of the 34x34 column footprint: s_h[(z+1)*34 + (x+1)]
+    v4::Smem<kGreedy>& sm = *reinterpret_cast<v4::Smem<kGreedy>*>(smem_raw);
+    __shared__ short s_h[34 * 34];   // heights of the column footprint: s_h[(z+1)*34 + (x+1)]  (|h-256| <= 720)
     __shared__ int s_red[2 * kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t chunk = blockIdx.x;
     if (chunk >= n) return;
     const vxp_coord c = coords[chunk];
     const TerrainKeys tk = terrain_keys(seed);
+    v4::Prof prof;
+    prof.start(tid == 0);
     if (tid == 0) sm.ones = kFull;
 
     int hmin = INT_MAX, hmax = INT_MIN;
@@ -144,7 +118,7 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t s
             hmin = min(hmin, h);
             hmax = max(hmax, h);
         }
-        s_h[i] = h;
+        s_h[i] = (short)h;
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -167,7 +141,7 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t s
 #pragma unroll 2
     for (int j = tid; j < 4096; j += kThreads) {
         const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
-        const int* hp = s_h + (z + 1) * 34 + x0 + 1;
+        const short* hp = s_h + (z + 1) * 34 + x0 + 1;
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
@@ -181,7 +155,7 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t s
         else if (face == 1) { zz = r; Y = Y0 + 32; dst = (r + 1) * 34 + 33; }
         else if (face == 2) { zz = -1; Y = Y0 + r; dst = 0 * 34 + (r + 1); }
         else { zz = 32; Y = Y0 + r; dst = 33 * 34 + (r + 1); }
-        const int* hp = s_h + (zz + 1) * 34 + 1;
+        const short* hp = s_h + (zz + 1) * 34 + 1;
         uint32_t bits = 0;
 #pragma unroll 8
         for (int x = 0; x < 32; ++x) bits |= (uint32_t)(Y <= hp[x]) << x;
@@ -196,30 +170,32 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t s
         sm.xh[face][z] = bits;
     }
     __syncthreads();
+    prof.mark(0);
 
-    const bool uniform = build_occupancy(sm);
-    if (kGreedy && !uniform) build_equality(sm);
-    __syncthreads();
-    build_masks<kGreedy>(sm, uniform);
-    __syncthreads();
-    const int* hcol = s_h;
-    emit_chunk<kGreedy>(sm, chunk, uniform, out, [hcol, Y0](int idx) -> uint32_t {
+    uint32_t v_or = 0, v_and = kFull, o_and = kFull;
+#pragma unroll 1
+    for (int s = 0; s < v4::kSlabs; ++s) v4::convert_slab(sm, s, v_or, v_and, o_and);
+    const v4::ChunkFlags fl = v4::reduce_flags(sm, v_or, v_and, o_and);
+    prof.mark(1);
+    const short* hcol = s_h;
+    v4::mesh_tail<kGreedy>(sm, chunk, fl, out, [hcol, Y0](int idx) -> uint32_t {
         const int x = idx & 31, y = (idx >> 5) & 31, z = idx >> 10;
         return terrain_block(hcol[(z + 1) * 34 + x + 1], Y0 + y);
-    });
+    }, prof);
 }
 
 // ====================================================================== launchers
 
-static cudaError_t set_smem(const void* fn) {
-    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem));
+template <class K>
+static cudaError_t set_smem(K fn, size_t bytes) {
+    return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 cudaError_t configure_device() {
-    cudaError_t e = set_smem((const void*)mesh_kernel<false>);
-    if (e == cudaSuccess) e = set_smem((const void*)mesh_kernel<true>);
-    if (e == cudaSuccess) e = set_smem((const void*)terrain_mesh_kernel<false>);
-    if (e == cudaSuccess) e = set_smem((const void*)terrain_mesh_kernel<true>);
+    cudaError_t e = set_smem(v4::mesh_kernel<false>, sizeof(v4::Smem<false>));
+    if (e == cudaSuccess) e = set_smem(v4::mesh_kernel<true>, sizeof(v4::Smem<true>));
+    if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel<false>, sizeof(v4::Smem<false>));
+    if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel<true>, sizeof(v4::Smem<true>));
     return e;
 }
 
@@ -237,32 +213,48 @@ cudaError_t launch_pattern_fill(const vxp_coord* d_coords, uint32_t n, int patte
     return cudaGetLastError();
 }
 
+static v4::MeshOut mesh_out(const vxp_mesh_dev& o) {
+    return v4::MeshOut{reinterpret_cast<unsigned long long*>(o.verts), o.indices, o.meta,
+                       reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads};
+}
+
 cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, int greedy,
-                        const vxp_mesh_dev& o, cudaStream_t stream) {
+                        const vxp_mesh_dev& o, const BoundaryScratch& scratch, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
     if (e != cudaSuccess || n == 0) return e;
-    MeshOut out{reinterpret_cast<unsigned long long*>(o.verts), o.indices, o.meta,
-                reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads};
+    const v4::Bnd bnd{scratch.tags, scratch.planes, scratch.epoch};
     if (greedy)
-        mesh_kernel<true><<<n, kThreads, sizeof(MeshSmem), stream>>>(d_voxels, d_nbr6, n, out);
+        v4::mesh_kernel<true><<<n, kThreads, sizeof(v4::Smem<true>), stream>>>(d_voxels, d_nbr6, n, mesh_out(o), bnd);
     else
-        mesh_kernel<false><<<n, kThreads, sizeof(MeshSmem), stream>>>(d_voxels, d_nbr6, n, out);
+        v4::mesh_kernel<false><<<n, kThreads, sizeof(v4::Smem<false>), stream>>>(d_voxels, d_nbr6, n, mesh_out(o), bnd);
     return cudaGetLastError();
 }
+
+size_t boundary_tag_bytes(uint32_t n) { return (size_t)n * sizeof(uint32_t); }
+size_t boundary_plane_bytes(uint32_t n) { return (size_t)n * 64 * sizeof(unsigned long long); }
+
+#ifdef VXP_PROFILE
+// profiling build only: read (and clear) the per-CTA phase counters of the mesh kernels
+extern "C" int vxp_debug_read_prof(unsigned long long* out, int max_ctas) {
+    const int ctas = max_ctas < v4::kProfCtas ? max_ctas : v4::kProfCtas;
+    const size_t bytes = sizeof(unsigned long long) * v4::kProfSlots * (size_t)ctas;
+    if (cudaMemcpyFromSymbol(out, v4::g_prof, bytes) != cudaSuccess) return -1;
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, v4::g_prof) != cudaSuccess) return -2;
+    if (cudaMemset(sym, 0, sizeof(unsigned long long) * v4::kProfSlots * v4::kProfCtas) != cudaSuccess) return -3;
+    return v4::kProfSlots;
+}
+#endif
 
 cudaError_t launch_terrain_mesh(const vxp_coord* d_coords, uint32_t n, uint64_t seed, int greedy,
                                 const vxp_mesh_dev& o, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
     if (e != cudaSuccess || n == 0) return e;
-    MeshOut out{reinterpret_cast<unsigned long long*>(o.verts), o.indices, o.meta,
-                reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads};
     if (greedy)
-        terrain_mesh_kernel<true><<<n, kThreads, sizeof(MeshSmem), stream>>>(d_coords, n, seed, out);
+        terrain_mesh_kernel<true><<<n, kThreads, sizeof(v4::Smem<true>), stream>>>(d_coords, n, seed, mesh_out(o));
     else
-        terrain_mesh_kernel<false><<<n, kThreads, sizeof(MeshSmem), stream>>>(d_coords, n, seed, out);
+        terrain_mesh_kernel<false><<<n, kThreads, sizeof(v4::Smem<false>), stream>>>(d_coords, n, seed, mesh_out(o));
     return cudaGetLastError();
 }
-
-size_t mesh_smem_bytes() { return sizeof(MeshSmem); }
 
 } // namespace vxp

@@ -5,16 +5,26 @@
 #include "../../include/vxp.h"
 
 namespace vxp {
+// Context-owned scratch of the mesh kernel (vxp_mesh4.cuh, "halo"): per meshed chunk one tag word and
+// two 32-word x-boundary bit planes stored as epoch-stamped 64-bit words.  Both areas must be zero-filled
+// when allocated; epoch is a per-context launch counter in [1, 2^30) (the areas are re-zeroed when it
+// wraps).  tags == nullptr disables the exchange.
+struct BoundaryScratch {
+    uint32_t* tags;
+    unsigned long long* planes;
+    uint32_t epoch;
+};
+size_t boundary_tag_bytes(uint32_t n);
+size_t boundary_plane_bytes(uint32_t n);
+
 // per-device one-time setup (opt-in shared memory size); call with the device current
 cudaError_t configure_device();
 cudaError_t launch_terrain_fill(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
                                 cudaStream_t stream);
 cudaError_t launch_pattern_fill(const vxp_coord* d_coords, uint32_t n, int pattern, uint16_t* d_voxels,
                                 cudaStream_t stream);
-// both zero *total_quads first (one memset node), then launch one kernel
 cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, int greedy,
-                        const vxp_mesh_dev& out, cudaStream_t stream);
+                        const vxp_mesh_dev& out, const BoundaryScratch& scratch, cudaStream_t stream);
 cudaError_t launch_terrain_mesh(const vxp_coord* d_coords, uint32_t n, uint64_t seed, int greedy,
                                 const vxp_mesh_dev& out, cudaStream_t stream);
-size_t mesh_smem_bytes();
 }  // namespace vxp

@@ -1,0 +1,744 @@
+// vxp_mesh4.cuh — per-chunk meshing pipeline, generation 4 (SPEC §2-§5).
+//
+// One CTA (256 threads, ~70 KiB of shared memory, three CTAs per SM) owns one chunk:
+//
+//   tile      64 KiB, four 16 KiB slabs landed by bulk TMA copies (or written by the fused
+//             terrain generator); converted slab by slab as the copies complete
+//     -> occ  occupancy bit volume (bit x of word (y,z)) plus a one-voxel halo
+//     -> eq   id-equality bit volumes EX/EY/EZ, greedy only, computed from the tile for the
+//             rows that carry a visible face and held in registers until the tile is dead
+//     -> mask six face-mask sets in plane orientation (X planes through warp bit transposes)
+//     -> culled: popcount + block scan;  greedy: bit-parallel row sweep, one thread per
+//        plane, 32 constant-cost row steps (no per-quad inner loops, no divergence on
+//        quad count), finished quads staged through a shared-memory cursor
+//     -> one 32-byte vertex store per quad, coalesced 8-byte index stores.
+//
+// After the equality pass the tile is dead and its 64 KiB are re-used for eq / mask /
+// staging, which is what lets three CTAs share an SM.
+//
+// Halo.  The +-X halo of a chunk is one u16 out of every 64-byte row of the neighbour:
+// 1024 sectors per face if gathered from the voxels.  Instead every CTA publishes the six
+// boundary bit planes of its own chunk (768 B, or just an "all air" / "all solid" tag) to a
+// context-owned scratch area as soon as its occupancy is known, and a neighbour that finds
+// the tag of the current launch reads those 128-byte planes; otherwise it gathers from the
+// voxels.  Nobody ever waits, so there is no ordering requirement between CTAs, and both
+// paths yield the same bits.
+#pragma once
+#include "vxp_device.cuh"
+#include "../../include/vxp.h"
+
+namespace vxp {
+namespace v4 {
+
+constexpr int kPlaneWords = 32 * kPad;   // 1056 words per padded 32x32 word plane set
+constexpr int kSlabBytes = 16384;        // 8 z-layers
+constexpr int kSlabs = 4;
+
+// ---- optional per-phase cycle accounting (profiling build only: -DVXP_PROFILE, libvxp_prof.so)
+#ifdef VXP_PROFILE
+constexpr int kProfSlots = 16;
+constexpr int kProfCtas = 8192;
+__device__ unsigned long long g_prof[kProfCtas][kProfSlots];
+struct Prof {
+    long long t;
+    bool on;
+    __device__ __forceinline__ void start(bool enable) { on = enable && blockIdx.x < kProfCtas; t = clock64(); }
+    __device__ __forceinline__ void mark(int slot) {
+        // plain stores only (one chunk per CTA, every slot written at most once): a read-modify-write
+        // would put a global round trip into every phase it tries to measure
+        if (on) { const long long n = clock64(); g_prof[blockIdx.x][slot] = (unsigned long long)(n - t); t = n; }
+    }
+    __device__ __forceinline__ void count(int slot, unsigned long long v = 1ull) { if (on) g_prof[blockIdx.x][slot] = v; }
+};
+#else
+struct Prof {
+    __device__ __forceinline__ void start(bool) {}
+    __device__ __forceinline__ void mark(int) {}
+    __device__ __forceinline__ void count(int, unsigned long long = 1ull) {}
+};
+#endif
+
+// ---- boundary summaries (context-owned scratch, one entry per meshed chunk)
+constexpr uint32_t kTagAir = 1u, kTagSolid = 2u;   // low 2 bits of a tag; the rest is the launch epoch
+struct Bnd {
+    uint32_t* tags;               // n words: epoch<<2 | kTag*  (only chunks that are all air / all solid)
+    unsigned long long* planes;   // n x 2 x 32 words: epoch<<32 | bits; [0] = the chunk's x=0 layer, [1] = x=31 (word z, bit y)
+    uint32_t epoch;               // in [1, 2^30)
+};
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- shared memory
+template <bool kGreedy>
+struct Post;   // what lives in the tile's 64 KiB once the tile is dead
+template <>
+struct Post<false> {
+    static constexpr int kCap = (kTileBytes - 192 * kPad * 4) / 4 - 192 * 32 - kThreads;   // 3648 staged quad records
+    uint32_t mask[192 * kPad];   // mask[(f*32+s)*33 + v] bit u: face f of cell (u,v) in slice s visible
+    uint32_t rows[192 * 32];     // non-empty mask rows: row | (ordinal of its first quad inside its thread's share) << 13
+    uint32_t tbase[kThreads];    // ordinal of the first quad of each thread's share
+    uint32_t staging[kCap];
+};
+template <>
+struct Post<true> {
+    static constexpr int kCap = (kTileBytes - (192 * kPad + 5 * kPlaneWords) * 4) / 4;   // 4768
+    uint32_t ex[kPlaneWords];    // ex[z*33+y] bit x = (id(x,y,z) == id(x-1,y,z))   (bit 0 unused)
+    uint32_t ey[kPlaneWords];    // ey[z*33+y] bit x = (id(x,y,z) == id(x,y-1,z))   (row y=0 unused)
+    uint32_t ez[kPlaneWords];    // ez[z*33+y] bit x = (id(x,y,z) == id(x,y,z-1))   (layer z=0 unused)
+    uint32_t ht[kPlaneWords];    // X planes: ht[x*33+z] bit y = ey transposed
+    uint32_t vt[kPlaneWords];    // X planes: vt[x*33+z] bit y = ez transposed
+    uint32_t mask[192 * kPad];
+    uint32_t staging[kCap];
+};
+
+template <bool kGreedy>
+struct __align__(128) Smem {
+    union {
+        uint16_t vox[VXP_CHUNK_VOXELS];   // [z][y][x]
+        Post<kGreedy> post;
+    } tile;
+    uint32_t occ[34 * 34];      // occ[(z+1)*34 + (y+1)], bit x; rows/layers -1 and 32 are the halo
+    uint32_t xh[2][32];         // xh[0][z] bit y: voxel (-1,y,z) solid;  xh[1][z] bit y: voxel (32,y,z)
+    uint32_t actz[32];          // actz[z] bit y: row (y,z) carries at least one visible face
+    uint32_t wred[kWarps][4];
+    uint32_t scratch[kWarps + 1];
+    uint32_t cursor;            // staging fill level
+    uint32_t ones;              // 0xFFFFFFFF: stand-in equality row for single-id chunks
+    unsigned long long first;
+    unsigned long long mbar[kSlabs];
+};
+static_assert(sizeof(Post<false>) <= kTileBytes && sizeof(Post<true>) <= kTileBytes, "post-tile layout overflows the tile");
+static_assert(3 * (sizeof(Smem<true>) + 1024) <= 227 * 1024 + 1024, "three CTAs per SM need <= ~75 KiB each");
+
+struct MeshOut {
+    unsigned long long* verts;
+    uint32_t* indices;
+    vxp_chunk_meta* meta;
+    unsigned long long* total;
+    unsigned long long cap;
+};
+
+// 8 consecutive u16 -> 8 bits (bit j = element j non-zero): 4 VIMNMX.U16x2 + 3 LEA + 2 logic
+__device__ __forceinline__ uint32_t nz8(uint4 q) {
+    const uint32_t a = __vminu2(q.x, 0x00010001u), b = __vminu2(q.y, 0x00010001u);
+    const uint32_t c = __vminu2(q.z, 0x00010001u), d = __vminu2(q.w, 0x00010001u);
+    const uint32_t acc = (a + (b << 2)) + ((c + (d << 2)) << 4);   // even elements: bits 0,2,4,6; odd: 16,18,20,22
+    return (acc | (acc >> 15)) & 0xFFu;
+}
+
+struct ChunkFlags {
+    bool any_solid, all_solid, single_id;
+};
+
+// ------------------------------------------------------------------ tile -> occupancy
+// Convert slab s (layers 8s..8s+7); accumulates the per-thread flag words.
+template <bool kGreedy>
+__device__ __forceinline__ void convert_slab(Smem<kGreedy>& sm, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and) {
+    const int tid = threadIdx.x;
+    const uint4* slab = reinterpret_cast<const uint4*>(sm.tile.vox) + s * (kSlabBytes / 16);
+    unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = tid + k * kThreads;                 // uint4 index inside the slab: row*4 + piece
+        const uint4 q = slab[idx];                          // a warp reads 512 contiguous bytes
+        const int row = s * 256 + (idx >> 2), p = idx & 3;  // row = z*32 + y
+        const uint32_t bits = nz8(q);
+        v_or |= q.x | q.y | q.z | q.w;
+        v_and &= q.x & q.y & q.z & q.w;
+        o_and &= bits;
+        occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)bits;
+    }
+}
+// Block-wide flags; contains the barrier that publishes the occupancy interior.
+template <bool kGreedy>
+__device__ __forceinline__ ChunkFlags reduce_flags(Smem<kGreedy>& sm, uint32_t v_or, uint32_t v_and, uint32_t o_and) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v_or = __reduce_or_sync(kFull, v_or);
+    v_and = __reduce_and_sync(kFull, v_and);
+    o_and = __reduce_and_sync(kFull, o_and);
+    if (lane == 0) { sm.wred[warp][0] = v_or; sm.wred[warp][1] = v_and; sm.wred[warp][2] = o_and; }
+    __syncthreads();
+    uint32_t a = 0, b = kFull, c = kFull;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { a |= sm.wred[w][0]; b &= sm.wred[w][1]; c &= sm.wred[w][2]; }
+    ChunkFlags f;
+    f.any_solid = a != 0;
+    f.all_solid = (c & 0xFFu) == 0xFFu;
+    f.single_id = a == b && (a & 0xFFFFu) == (a >> 16);   // every u16 of the chunk is the same value
+    return f;
+}
+
+// ------------------------------------------------------------------ halo
+// +-Y / +-Z faces: one 64-byte row of the neighbour per lane, fetched by warps 2..5 at kernel start
+// (so the round trip overlaps the tile load) and turned into halo words after the conversion.
+struct HaloRows {
+    uint4 q[4];
+};
+__device__ __forceinline__ void issue_yz_halo(HaloRows& h, const uint16_t* __restrict__ voxels, int nb) {
+    const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;
+    h.q[0] = h.q[1] = h.q[2] = h.q[3] = make_uint4(0, 0, 0, 0);
+    if (f < 2 || f >= 6 || nb < 0) return;
+    const int row = f == 2 ? lane * 32 + 31 : f == 3 ? lane * 32 : f == 4 ? 31 * 32 + lane : lane;   // (z*32 + y) in the neighbour
+    const uint4* r4 = reinterpret_cast<const uint4*>(voxels + (size_t)nb * VXP_CHUNK_VOXELS + row * 32);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h.q[k] = __ldg(r4 + k);
+}
+
+// +-X faces: the chunk's own x=0 / x=31 boundary planes (word z, bit y) are published to the
+// context scratch as self-validating 64-bit words (launch epoch in the high half), so readers
+// need no ordering and a single round trip; chunks that are all air / all solid publish one
+// tag word instead.
+template <bool kGreedy>
+__device__ __forceinline__ void publish_boundary(const Smem<kGreedy>& sm, const Bnd& bnd, uint32_t chunk, ChunkFlags fl) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!fl.any_solid || fl.all_solid) {
+        if (tid == kThreads - 32) st_relaxed_u32(bnd.tags + chunk, bnd.epoch << 2 | (fl.any_solid ? kTagSolid : kTagAir));
+        return;
+    }
+    unsigned long long* dst = bnd.planes + (size_t)chunk * 64;
+    const unsigned long long hi_epoch = (unsigned long long)bnd.epoch << 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int z = warp * 4 + k;
+        const uint32_t c = sm.occ[(z + 1) * 34 + lane + 1];
+        const uint32_t lo = __ballot_sync(kFull, c & 1u), hi = __ballot_sync(kFull, c >> 31);
+        if (lane == 0) {
+            st_relaxed_u64(dst + z, hi_epoch | lo);
+            st_relaxed_u64(dst + 32 + z, hi_epoch | hi);
+        }
+    }
+}
+
+// Fill the halo of sm.occ / sm.xh: warp f < 6 produces the 32 words of face f.  Returns (per
+// thread) whether any halo bit this thread produced is air.  Contains no barrier.
+// nb = neighbour index of face f = warp index (loaded by the caller before the tile wait).
+constexpr int kPlanePolls = 3;   // bounded re-reads of a boundary plane that is not there yet (never a wait-for)
+template <bool kGreedy>
+__device__ __forceinline__ bool load_halo(Smem<kGreedy>& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n,
+                                          const Bnd& bnd, const HaloRows& rows, Prof& prof) {
+    const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
+    if (f >= 6) return false;
+    uint32_t word = 0;
+    if (f >= 2) {
+        if (nb >= 0) word = nz8(rows.q[0]) | nz8(rows.q[1]) << 8 | nz8(rows.q[2]) << 16 | nz8(rows.q[3]) << 24;
+        sm.occ[f == 2 ? (lane + 1) * 34 : f == 3 ? (lane + 1) * 34 + 33 : f == 4 ? lane + 1 : 33 * 34 + lane + 1] = word;
+        return word != kFull;
+    }
+    if (nb >= 0) {
+        bool have = false;
+        if (bnd.tags && (uint32_t)nb < n) {
+            const uint32_t* tagp = bnd.tags + nb;
+            const unsigned long long* planep = bnd.planes + (size_t)nb * 64 + (f ^ 1) * 32 + lane;
+            for (int t = 0; t < kPlanePolls && !have; ++t) {
+                const uint32_t tag = ld_relaxed_u32(tagp);             // both loads in flight together
+                const unsigned long long pw = ld_relaxed_u64(planep);
+                if ((tag >> 2) == bnd.epoch) {                          // all air / all solid neighbour
+                    word = (tag & 3u) == kTagSolid ? kFull : 0u;
+                    have = true;
+                } else if (__all_sync(kFull, (uint32_t)(pw >> 32) == bnd.epoch)) {
+                    word = (uint32_t)pw;
+                    have = true;
+                }
+                if (lane == 0) prof.count(15, (unsigned long long)(t + 1));
+            }
+            if (lane == 0) prof.count(have ? 12 : 13);
+            prof.mark(14);
+        }
+        if (!have) {                                      // gather from the neighbour's voxels: one u16 per 64-byte row
+            const uint16_t* nv = voxels + (size_t)nb * VXP_CHUNK_VOXELS + (f ? 0 : 31) + 32 * lane;
+#pragma unroll 8
+            for (int z = 0; z < 32; ++z) {
+                const uint32_t v = __ldg(nv + 1024 * z);
+                const uint32_t w = __ballot_sync(kFull, v != 0);
+                if (lane == z) word = w;
+            }
+        }
+    }
+    sm.xh[f][lane] = word;
+    return word != kFull;
+}
+
+// ------------------------------------------------------------------ active rows
+// actz[z] bit y = row (y,z) has a solid voxel with an air neighbour (halo included).
+template <bool kGreedy>
+__device__ __forceinline__ void build_active(Smem<kGreedy>& sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int z = warp * 4 + k, y = lane;
+        const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
+        const uint32_t c = o[0];
+        const uint32_t lo = (sm.xh[0][z] >> y) & 1u, hi = (sm.xh[1][z] >> y) & 1u;
+        const uint32_t buried = o[-1] & o[1] & o[-34] & o[34] & ((c << 1) | lo) & ((c >> 1) | (hi << 31));
+        const uint32_t act = __ballot_sync(kFull, (c & ~buried) != 0);
+        if (lane == 0) sm.actz[z] = act;
+    }
+}
+
+// ------------------------------------------------------------------ tile -> EX / EY / EZ (into registers)
+// res[k] of a thread with piece p = lane&3 holds, for row (idx>>2) of item k: p=0 the EX word,
+// p=1 EY, p=2 EZ.  Rows without a visible face are skipped (their words are never consulted).
+template <bool kGreedy>
+__device__ __forceinline__ void equality_to_regs(const Smem<kGreedy>& sm, uint32_t (&res)[16]) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int p = lane & 3;
+    const uint4* tile4 = reinterpret_cast<const uint4*>(sm.tile.vox);
+    const uint32_t selA = (p & 1) ? 0x3715u : 0x6240u;   // 4x4 byte transpose across the 4 lanes of a row
+    const uint32_t selB = (p & 2) ? 0x3276u : 0x5410u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int idx = tid + k * kThreads;
+        const int row = idx >> 2, z = row >> 5, y = row & 31;
+        res[k] = 0;
+        // the warp's 8 rows are y0..y0+7 of one layer
+        if (((sm.actz[z] >> (y & 24)) & 0xFFu) == 0) continue;   // warp-uniform
+        const uint4 q = tile4[idx];
+        const uint32_t leftw = __shfl_up_sync(kFull, q.w, 1);
+        const uint4 px = make_uint4(prev16(leftw, q.x), prev16(q.x, q.y), prev16(q.y, q.z), prev16(q.z, q.w));
+        uint32_t w = (~nz8(xor4(q, px))) & 0xFFu;
+        if (y > 0) w |= ((~nz8(xor4(q, tile4[idx - 4]))) & 0xFFu) << 8;
+        if (z > 0) w |= ((~nz8(xor4(q, tile4[idx - 128]))) & 0xFFu) << 16;
+        uint32_t t = __shfl_xor_sync(kFull, w, 1);
+        w = __byte_perm(w, t, selA);
+        t = __shfl_xor_sync(kFull, w, 2);
+        res[k] = __byte_perm(w, t, selB);
+    }
+}
+__device__ __forceinline__ void equality_store(Post<true>& post, const uint32_t (&res)[16]) {
+    const int tid = threadIdx.x, p = tid & 3;
+    if (p == 3) return;
+    uint32_t* const dst = p == 0 ? post.ex : p == 1 ? post.ey : post.ez;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int row = (tid + k * kThreads) >> 2;
+        dst[(row >> 5) * kPad + (row & 31)] = res[k];
+    }
+}
+
+// ------------------------------------------------------------------ occupancy -> face masks
+// Returns the OR of every mask word this thread produced.
+template <bool kGreedy>
+__device__ __forceinline__ uint32_t build_masks(Smem<kGreedy>& sm, bool with_eq) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* mask = sm.tile.post.mask;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int z = k * kWarps + warp, y = lane;
+        const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
+        const uint32_t c = o[0];
+        const uint32_t my = c & ~o[-1], py = c & ~o[+1], mz = c & ~o[-34], pz = c & ~o[+34];
+        mask[(2 * 32 + y) * kPad + z] = my;    // -Y : slice y, row z
+        mask[(3 * 32 + y) * kPad + z] = py;    // +Y
+        mask[(4 * 32 + z) * kPad + y] = mz;    // -Z : slice z, row y
+        mask[(5 * 32 + z) * kPad + y] = pz;    // +Z
+        const uint32_t lo = (sm.xh[0][z] >> y) & 1u, hi = (sm.xh[1][z] >> y) & 1u;
+        uint32_t vxm = c & ~((c << 1) | lo);            // -X visible, bit x
+        uint32_t vxq = c & ~((c >> 1) | (hi << 31));    // +X visible, bit x
+        acc |= my | py | mz | pz | vxm | vxq;
+        // transpose (lane=y, bit=x) -> (lane=x, bit=y): X planes have u=y, v=z, slice x
+        const bool anym = __any_sync(kFull, vxm != 0), anyq = __any_sync(kFull, vxq != 0);
+        if (anym) vxm = transpose32(vxm, lane);
+        if (anyq) vxq = transpose32(vxq, lane);
+        mask[(0 * 32 + lane) * kPad + z] = vxm;
+        mask[(1 * 32 + lane) * kPad + z] = vxq;
+        if constexpr (kGreedy) {
+            if (with_eq && (anym || anyq)) {
+                sm.tile.post.ht[lane * kPad + z] = transpose32(sm.tile.post.ey[z * kPad + y], lane);
+                sm.tile.post.vt[lane * kPad + z] = transpose32(sm.tile.post.ez[z * kPad + y], lane);
+            }
+        }
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------ greedy sweep (one thread = one plane)
+// Bit-parallel evaluation of the SPEC §4 greedy rule.  After row v-1 every set cell of that row
+// belongs to exactly one active run (S = start bits, E = end bits, cover C = mask row v-1).
+// Row v: a run survives iff all its cells are set in row v with the id of the cell above
+// (G = M & V); survivors are found with one carry chain upwards (segmented AND-reduce) and
+// spread back over their run with one carry chain on the bit-reversed words.  Runs that do not
+// survive are finished quads; the cells of row v not covered by survivors start new runs,
+// split where the id changes (H).  r0..r4 hold the start row of the run that starts at each
+// column, bit-sliced.
+struct Sweep {
+    const uint32_t* m;   // this plane's 32 mask rows
+    const uint32_t* hb;  // equality rows along u  (bit u: cell u has the id of cell u-1)
+    const uint32_t* vb;  // equality rows along v  (bit u: cell (u,v) has the id of (u,v-1))
+    int hs, vs;          // row strides of hb / vb
+    uint32_t C, S, E, r0, r1, r2, r3, r4;
+    uint32_t base;       // f<<15 | s<<10
+};
+
+template <bool kGreedy>
+__device__ __forceinline__ void sweep_init(Sweep& st, Smem<kGreedy>& sm, bool with_eq) {
+    const int tid = threadIdx.x;
+    const int f = tid >> 5, s = tid & 31;
+    st.C = st.S = st.E = st.r0 = st.r1 = st.r2 = st.r3 = st.r4 = 0;
+    st.base = (uint32_t)f << 15 | (uint32_t)s << 10;
+    st.m = sm.tile.post.mask + (tid < 192 ? tid : 0) * kPad;
+    st.hb = st.vb = &sm.ones;
+    st.hs = st.vs = 0;
+    if constexpr (kGreedy) {
+        if (with_eq) {
+            Post<true>& P = sm.tile.post;
+            if (f < 2) { st.hb = P.ht + s * kPad; st.hs = 1; st.vb = P.vt + s * kPad; st.vs = 1; }        // X planes: u=y, v=z
+            else if (f < 4) { st.hb = P.ex + s; st.hs = kPad; st.vb = P.ez + s; st.vs = kPad; }           // Y planes: u=x, v=z
+            else { st.hb = P.ex + s * kPad; st.hs = 1; st.vb = P.ey + s * kPad; st.vs = 1; }              // Z planes: u=x, v=y
+        }
+    }
+}
+
+// Stage the runs (dS, dE: start / end bits, pairwise in order) that ended before row v.
+__device__ __forceinline__ void sweep_emit(const Sweep& st, uint32_t dS, uint32_t dE, int v, uint32_t* staging,
+                                           uint32_t cap, uint32_t* cursor) {
+    if (dS == 0) return;
+    uint32_t pos = atomicAdd(cursor, (uint32_t)__popc(dS));   // one reservation per row step, not per quad
+#ifdef VXP_EXP_NO_EMIT
+    if (pos != 0xFFFFFFFFu) return;   // timing experiment: the sweep without its per-quad loop (wrong output)
+#endif
+    const uint32_t tail = st.base | (uint32_t)(v - 1) << 23;
+    do {
+        const int u = __ffs(dS) - 1, e = __ffs(dE) - 1;
+        dS &= dS - 1;
+        dE &= dE - 1;
+        const uint32_t v0 = ((st.r0 >> u) & 1u) | ((st.r1 >> u) & 1u) << 1 | ((st.r2 >> u) & 1u) << 2 |
+                            ((st.r3 >> u) & 1u) << 3 | ((st.r4 >> u) & 1u) << 4;
+        // u | v0<<5 | s<<10 | f<<15 | (w-1)<<18 | (h-1)<<23 with h-1 = v-1-v0
+        const uint32_t rec = tail + (uint32_t)u + (v0 << 5) + ((uint32_t)(e - u) << 18) - (v0 << 23);
+        if (pos < cap) staging[pos] = rec;
+        ++pos;
+    } while (dS);
+}
+
+
+// One row step (v in [0,32]); v == 32 flushes the runs still active after the last row.
+__device__ __forceinline__ void sweep_step(Sweep& st, int v, uint32_t* staging, uint32_t cap, uint32_t* cursor) {
+    if (v == 32) {
+        sweep_emit(st, st.S, st.E, 32, staging, cap, cursor);
+        st.S = st.E = st.C = 0;
+        return;
+    }
+    const uint32_t Mv = st.m[v];
+    if ((Mv | st.C) == 0) return;
+    const uint32_t Hv = st.hb[v * st.hs], Vv = st.vb[v * st.vs];
+    uint32_t Cs = 0;
+    if (st.C) {
+        const uint32_t X = st.C & Mv & Vv;
+        const uint32_t T = (X & ~st.E) + st.S;
+        const uint32_t Es = T & st.E & X;                       // end bits of the surviving runs
+        const uint32_t P = __brev(st.C) & ~__brev(st.S);
+        const uint32_t Q = P + __brev(Es);
+        Cs = __brev(Q ^ P);                                     // their cover
+        sweep_emit(st, st.S & ~Cs, st.E & ~Cs, v, staging, cap, cursor);
+    }
+    const uint32_t R = Mv & ~Cs;
+    const uint32_t NS = R & ~((R << 1) & Hv);
+    const uint32_t NE = R & ~((R >> 1) & (Hv >> 1));
+    st.S = (st.S & Cs) | NS;
+    st.E = (st.E & Cs) | NE;
+    st.C = Mv;
+    st.r0 = (st.r0 & ~NS) | ((v & 1) ? NS : 0u);
+    st.r1 = (st.r1 & ~NS) | ((v & 2) ? NS : 0u);
+    st.r2 = (st.r2 & ~NS) | ((v & 4) ? NS : 0u);
+    st.r3 = (st.r3 & ~NS) | ((v & 8) ? NS : 0u);
+    st.r4 = (st.r4 & ~NS) | ((v & 16) ? NS : 0u);
+}
+
+// ------------------------------------------------------------------ staged records -> buffers
+__device__ __forceinline__ void st_global_v4u64(void* p, unsigned long long a, unsigned long long b,
+                                                unsigned long long c, unsigned long long d) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+// chunk-local voxel index of the origin cell of a staged record
+__device__ __forceinline__ int rec_origin_voxel(uint32_t rec) {
+    const uint32_t u = rec & 31u, v = (rec >> 5) & 31u, s = (rec >> 10) & 31u, axis = (rec >> 16) & 3u;
+    return (int)(s << (5u * axis) | u << (axis == 0 ? 5 : 0) | v << (axis == 2 ? 5 : 10));
+}
+// SPEC §5: the four vertices of a staged record with block id b, as one 32-byte store.
+__device__ __forceinline__ void store_quad(unsigned long long* dst, uint32_t rec, uint32_t b) {
+    const uint32_t u = rec & 31u, v = (rec >> 5) & 31u, s = (rec >> 10) & 31u, f = (rec >> 15) & 7u;
+    const uint32_t w = ((rec >> 18) & 31u) + 1u, h = ((rec >> 23) & 31u) + 1u, axis = f >> 1;
+    const uint32_t su = axis == 0 ? 6u : 0u, sv = axis == 2 ? 6u : 12u;          // bit offsets of U, V in word0
+    const uint32_t c0 = (s + (f & 1u)) << (6u * axis) | u << su | v << sv | f << 18;
+    const uint32_t du = w << su, dv = h << sv;
+    const bool flip = (0x19u >> f) & 1u;                                         // f in {0,3,4}: c0,c3,c2,c1
+    const uint32_t k1 = c0 + (flip ? dv : du), k3 = c0 + (flip ? du : dv), k2 = c0 + du + dv;
+    const unsigned long long w1 = (unsigned long long)(b | ((rec >> 18) & 0x3FFu) << 16) << 32;
+    st_global_v4u64(dst, w1 | c0, w1 | (k1 | 1u << 21), w1 | (k2 | 2u << 21), w1 | (k3 | 3u << 21));
+}
+
+// Writes quads [ord0, ord0+cnt) (chunk-local ordinals) of the chunk whose range starts at sm.first.
+// The first batch of records and block ids is fetched before `before_first()` + the optional
+// barrier, so the latency of the range reservation (a contended global atomic) overlaps the
+// id gather instead of preceding it.  Returns false if the chunk does not fit the arena.
+template <bool kGreedy, class IdFn, class Pre>
+__device__ __forceinline__ bool flush_staging(Smem<kGreedy>& sm, uint32_t cnt, uint32_t ord0, const MeshOut& out, IdFn id_of,
+                                              Pre before_first, bool barrier) {
+    const int tid = threadIdx.x;
+    const uint32_t* staging = sm.tile.post.staging;
+    uint32_t rec[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t i = tid + k * kThreads;
+        rec[k] = i < cnt ? staging[i] : 0u;
+        b[k] = i < cnt ? id_of(rec_origin_voxel(rec[k])) : 0u;
+    }
+    before_first();
+    if (barrier) __syncthreads();
+    const unsigned long long first = sm.first;
+    if (first == ~0ull) return false;
+    unsigned long long* const vdst = out.verts + (first + ord0) * 4;
+    // vertices: one thread per quad, one 32-byte store (a full sector)
+    for (uint32_t i0 = tid; i0 < cnt; i0 += 4 * kThreads) {
+        if (i0 != (uint32_t)tid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t i = i0 + k * kThreads;
+                rec[k] = i < cnt ? staging[i] : 0u;
+                b[k] = i < cnt ? id_of(rec_origin_voxel(rec[k])) : 0u;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = i0 + k * kThreads;
+            if (i < cnt) store_quad(vdst + (size_t)i * 4, rec[k], b[k]);
+        }
+    }
+    // indices: 8-byte pairs, three per quad -> a warp stores 256 contiguous bytes
+    uint32_t* const idst = out.indices + (first + ord0) * 6;
+    uint32_t j = (uint32_t)tid / 3u, part = (uint32_t)tid - 3u * j;
+    for (uint32_t i = tid; i < 3 * cnt; i += kThreads) {
+        const uint32_t b4 = 4 * (ord0 + j);
+        st_global_v2u32(idst + 2 * (size_t)i, b4 + (part == 0 ? 0u : part + 1u), b4 + (part == 0 ? 1u : part == 1 ? 2u : 0u));
+        j += kThreads / 3;                       // 256 = 85*3 + 1
+        if (++part == 3u) { part = 0u; ++j; }
+    }
+    return true;
+}
+
+// Thread 0: turn the result of the range reservation into sm.first and the chunk's meta entry.
+template <bool kGreedy>
+__device__ __forceinline__ void publish_range(Smem<kGreedy>& sm, uint32_t chunk, uint32_t Q, unsigned long long f,
+                                              const MeshOut& out) {
+    const bool fits = f + Q <= out.cap;
+    out.meta[chunk] = vxp_chunk_meta{fits ? (uint32_t)f : 0xFFFFFFFFu, Q};
+    sm.first = fits ? f : ~0ull;
+}
+
+// ------------------------------------------------------------------ masks -> quads -> buffers
+template <bool kGreedy, class IdFn>
+__device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bool with_eq, const MeshOut& out, IdFn id_of,
+                                           Prof& prof) {
+    const int tid = threadIdx.x;
+    constexpr uint32_t kCap = Post<kGreedy>::kCap;
+    uint32_t* const staging = sm.tile.post.staging;
+    const uint32_t* const mask = sm.tile.post.mask;
+    auto nothing = [] {};
+    if constexpr (!kGreedy) {
+        // ---- culled: every set bit is a quad.  Pass 1: thread t counts rows t, t+256, ... and lists the
+        // non-empty ones; pass 2: the threads share that list evenly, so the work is balanced however
+        // unevenly the faces are spread over the planes.
+        Post<false>& P = sm.tile.post;
+        if (tid == 0) sm.cursor = 0;
+        __syncthreads();
+        uint32_t mine = 0;
+#pragma unroll 4
+        for (int r = tid; r < 192 * 32; r += kThreads) {
+            const uint32_t c = __popc(mask[(r >> 5) * kPad + (r & 31)]);
+            if (c) P.rows[atomicAdd(&sm.cursor, 1u)] = (uint32_t)r | mine << 13;
+            mine += c;
+        }
+        uint32_t Q;
+        P.tbase[tid] = block_excl_scan(mine, sm.scratch, &Q);   // the scan's barriers also publish rows / cursor
+        if (Q == 0) {
+            if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+            return;
+        }
+        unsigned long long f = 0;
+        if (tid == 0) f = atomicAdd(out.total, (unsigned long long)Q);   // in flight while the records are staged
+        __syncthreads();
+        prof.mark(5);
+        const uint32_t nrows = sm.cursor;
+        for (uint32_t base = 0; base < Q; base += kCap) {
+            const uint32_t end = min(Q, base + kCap);
+            for (uint32_t i = tid; i < nrows; i += kThreads) {     // neighbours in the list are rows of similar density
+                const uint32_t d = P.rows[i], r = d & 8191u;
+                uint32_t bits = mask[(r >> 5) * kPad + (r & 31)];
+                uint32_t o = P.tbase[r & (kThreads - 1)] + (d >> 13);
+                const uint32_t rbase = (r >> 5) << 10 | (r & 31u) << 5;   // f<<15|s<<10|v<<5
+                if (o + __popc(bits) <= base || o >= end) continue;
+                while (bits) {
+                    const int u = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (o >= base && o < end) staging[o - base] = rbase | (uint32_t)u;
+                    ++o;
+                }
+            }
+            __syncthreads();
+            prof.mark(6);
+            bool fits;
+            if (base == 0) fits = flush_staging(sm, end, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); }, true);
+            else fits = flush_staging(sm, end - base, base, out, id_of, nothing, false);
+            if (!fits) return;
+            __syncthreads();
+            prof.mark(7);
+        }
+        return;
+    } else {
+        // ---- greedy: optimistic single sweep with everything staged
+        if (tid == 0) sm.cursor = 0;
+        __syncthreads();
+        Sweep st;
+        sweep_init(st, sm, with_eq);
+        if (tid < 192) {
+#pragma unroll 1
+            for (int v = 0; v <= 32; ++v) sweep_step(st, v, staging, kCap, &sm.cursor);
+        }
+        __syncthreads();
+        prof.mark(5);
+        const uint32_t Q = sm.cursor;
+        unsigned long long f = 0;
+        if (tid == 0) f = atomicAdd(out.total, (unsigned long long)Q);
+        auto publish = [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); };
+        if (Q <= kCap) {
+            flush_staging(sm, Q, 0, out, id_of, publish, true);
+            prof.mark(7);
+            return;
+        }
+        // heavy path (Q > kCap): sweep again, half of the planes per step (<= 96*32 quads), flushing each time
+        publish();
+        sweep_init(st, sm, with_eq);
+        uint32_t flushed = 0;
+#pragma unroll 1
+        for (int v = 0; v <= 32; ++v) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                __syncthreads();
+                if (tid == 0) sm.cursor = 0;
+                __syncthreads();
+                if (tid < 192 && (tid >= 96) == (half == 1)) sweep_step(st, v, staging, kCap, &sm.cursor);
+                __syncthreads();
+                const uint32_t cnt = sm.cursor;
+                if (!flush_staging(sm, cnt, flushed, out, id_of, nothing, false)) return;
+                flushed += cnt;
+            }
+        }
+        prof.mark(7);
+    }
+}
+
+
+// ------------------------------------------------------------------ shared tail of both kernels
+// Preconditions: occupancy interior + halo complete and published by a barrier; tile intact.
+template <bool kGreedy, class IdFn>
+__device__ __forceinline__ void mesh_tail(Smem<kGreedy>& sm, uint32_t chunk, ChunkFlags fl, const MeshOut& out, IdFn id_of,
+                                          Prof& prof) {
+    const int tid = threadIdx.x;
+    bool with_eq = false;
+    if constexpr (kGreedy) {
+        with_eq = !fl.single_id;
+        if (with_eq) {
+            build_active(sm);
+            __syncthreads();
+            uint32_t res[16];
+            equality_to_regs(sm, res);
+            __syncthreads();                     // the tile is dead from here on
+            equality_store(sm.tile.post, res);
+        }
+    }
+    __syncthreads();
+    prof.mark(3);
+    const bool any = __syncthreads_or(build_masks(sm, with_eq) != 0);
+    prof.mark(4);
+    if (!any) {
+        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+        prof.count(10);
+        return;
+    }
+    prof.count(11);
+    emit_chunk<kGreedy>(sm, chunk, with_eq, out, id_of, prof);
+}
+
+// ====================================================================== stored-chunk meshing
+// Slabs of the tile a CTA asks for before the first one has landed (measured on B200, config 2:
+// 1 -> 120 us, 2 -> 111 us, 4 -> 107 us per 4096 chunks: deeper is better, so the whole tile it is).
+#ifndef VXP_SLABS_IN_FLIGHT
+#define VXP_SLABS_IN_FLIGHT 4
+#endif
+constexpr int kSlabsInFlight = VXP_SLABS_IN_FLIGHT;
+template <bool kGreedy>
+__device__ __forceinline__ void issue_slab(Smem<kGreedy>& sm, const uint16_t* gvox, int s) {
+    mbar_expect_tx(&sm.mbar[s], kSlabBytes);
+    tma_load_1d(reinterpret_cast<unsigned char*>(sm.tile.vox) + s * kSlabBytes,
+                reinterpret_cast<const unsigned char*>(gvox) + s * kSlabBytes, kSlabBytes, &sm.mbar[s]);
+}
+
+template <bool kGreedy>
+__global__ void __launch_bounds__(kThreads, 3)
+mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, MeshOut out, Bnd bnd) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem<kGreedy>& sm = *reinterpret_cast<Smem<kGreedy>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= n) return;
+    const uint16_t* gvox = voxels + (size_t)chunk * VXP_CHUNK_VOXELS;
+    Prof prof;
+    prof.start(tid == 0);
+
+    if (tid == 0) {
+        sm.ones = kFull;
+#pragma unroll
+        for (int s = 0; s < kSlabs; ++s) mbar_init(&sm.mbar[s], 1);
+        fence_mbar_init();
+#pragma unroll
+        for (int s = 0; s < kSlabsInFlight; ++s) issue_slab(sm, gvox, s);
+    }
+    // neighbour of face (warp index), fetched while the tile is in flight
+    const int nb = (nbr6 && tid < 192) ? __ldg(nbr6 + 6 * (size_t)chunk + (tid >> 5)) : -1;
+    HaloRows rows;
+    issue_yz_halo(rows, voxels, nb);
+    __syncthreads();                            // barrier init visible to all waiters
+
+    uint32_t v_or = 0, v_and = kFull, o_and = kFull;
+#pragma unroll 1
+    for (int s = 0; s < kSlabs; ++s) {
+        mbar_wait(&sm.mbar[s], 0);
+        if (tid == 0 && s + kSlabsInFlight < kSlabs) issue_slab(sm, gvox, s + kSlabsInFlight);
+        convert_slab(sm, s, v_or, v_and, o_and);
+    }
+    prof.mark(0);
+    const ChunkFlags fl = reduce_flags(sm, v_or, v_and, o_and);   // barrier: occupancy interior published
+    prof.mark(1);
+    if (bnd.tags) publish_boundary(sm, bnd, chunk, fl);
+    if (!fl.any_solid) {                        // all air: no faces
+        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+        prof.count(8);
+        return;
+    }
+    const bool halo_air = __syncthreads_or(load_halo(sm, voxels, nb, n, bnd, rows, prof));   // barrier: halo published
+    prof.mark(2);
+    if (fl.all_solid && !halo_air) {            // buried: no faces
+        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+        prof.count(9);
+        return;
+    }
+    mesh_tail<kGreedy>(sm, chunk, fl, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
+}
+
+} // namespace v4
+} // namespace vxp
