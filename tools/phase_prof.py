@@ -12,7 +12,7 @@ coords = grid_coords((0, 0, 0), (16, 16, 16)); nbr = neighbour_table(coords)
 dc = torch.from_numpy(coords).cuda(); dn = torch.from_numpy(nbr).cuda()
 vox = [m.terrain_fill(dc, 42 + k) for k in range(4)]
 phases = ["convert", "flags+publish", "halo", "equality", "masks", "sweep/count", "stage", "flush"]
-counts = {8: "n_air", 9: "n_buried", 10: "n_nofaces", 11: "n_emit", 12: "xface_summary(warp0)", 13: "xface_gather(warp0)", 15: "xface_polls(warp0)"}
+counts = {8: "n_air", 9: "n_buried", 10: "n_nofaces", 11: "n_emit", 12: "xface_summary(warp0)", 13: "xface_gather(warp0)", 14: "greedy_heavy_path", 15: "xface_polls(warp0)"}
 NC = 8192
 lib.vxp_debug_read_prof.argtypes = [C.c_void_p, C.c_int]
 for mode, mn in ((CULLED, "culled"), (GREEDY, "greedy")):
@@ -25,8 +25,7 @@ for mode, mn in ((CULLED, "culled"), (GREEDY, "greedy")):
     e0.record(); m.mesh(vox[3], dn, mode, out=out); e1.record(); torch.cuda.synchronize()
     lib.vxp_debug_read_prof(buf.ctypes.data, NC)
     act = buf[:4096].astype(np.float64)
-    tot = act[:, :8].sum(1) + act[:, 14]
-    print(f"   publish+poll cycles (thread 0, chunks that polled): mean {act[act[:,15]>0,14].mean():.0f}")
+    tot = act[:, :8].sum(1)
     kinds = {"air": act[:, 8] > 0, "buried": act[:, 9] > 0, "emit": act[:, 11] > 0}
     print(f"== {mn}: kernel {e0.elapsed_time(e1)*1e3:.1f} us; per-CTA cycles mean {tot.mean():.0f} max {tot.max():.0f}")
     for kn, sel in kinds.items():
@@ -37,3 +36,8 @@ for mode, mn in ((CULLED, "culled"), (GREEDY, "greedy")):
             col = act[sel, i]
             if col.sum() > 0: print(f"        {nm:14s} mean {col.mean():8.0f}  max {col.max():8.0f}")
     for i, nm in counts.items(): print(f"   {nm:20s} {int(act[:, i].sum())}")
+    if mode == GREEDY:
+        wb = np.zeros((NC, 8), dtype=np.uint32)
+        lib.vxp_debug_read_prof_warp.argtypes = [C.c_void_p, C.c_int]; lib.vxp_debug_read_prof_warp(wb.ctypes.data, NC)
+        w = wb[:4096][kinds["emit"]].astype(np.float64)
+        print("   sweep cycles per warp (f = warp), emit chunks: mean", np.round(w.mean(0)).astype(int).tolist(), " mean of max", int(w.max(1).mean()))

@@ -234,6 +234,10 @@ size_t boundary_tag_bytes(uint32_t n) { return (size_t)n * sizeof(uint32_t); }
 size_t boundary_plane_bytes(uint32_t n) { return (size_t)n * 64 * sizeof(unsigned long long); }
 
 #ifdef VXP_PROFILE
+extern "C" int vxp_debug_read_prof_warp(unsigned int* out, int max_ctas) {
+    const int ctas = max_ctas < v4::kProfCtas ? max_ctas : v4::kProfCtas;
+    return cudaMemcpyFromSymbol(out, v4::g_prof_warp, sizeof(unsigned int) * 8 * (size_t)ctas) == cudaSuccess ? 8 : -1;
+}
 // profiling build only: read (and clear) the per-CTA phase counters of the mesh kernels
 extern "C" int vxp_debug_read_prof(unsigned long long* out, int max_ctas) {
     const int ctas = max_ctas < v4::kProfCtas ? max_ctas : v4::kProfCtas;

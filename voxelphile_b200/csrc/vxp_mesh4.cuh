@@ -39,6 +39,7 @@ constexpr int kSlabs = 4;
 constexpr int kProfSlots = 16;
 constexpr int kProfCtas = 8192;
 __device__ unsigned long long g_prof[kProfCtas][kProfSlots];
+__device__ unsigned int g_prof_warp[kProfCtas][8];   // per-warp cycles of the greedy sweep
 struct Prof {
     long long t;
     bool on;
@@ -96,13 +97,17 @@ struct Post<false> {
 template <>
 struct Post<true> {
     static constexpr int kCap = (kTileBytes - (192 * kPad + 5 * kPlaneWords) * 4) / 4;   // 4768
+    // "H" arrays (same id as the previous cell of the row) and the masks are needed until the quads are
+    // staged; the "V" arrays (same id as the cell of the previous row) only by the sweep, so they sit next
+    // to the staging area and join it afterwards (kArena words from ey on).
     uint32_t ex[kPlaneWords];    // ex[z*33+y] bit x = (id(x,y,z) == id(x-1,y,z))   (bit 0 unused)
+    uint32_t ht[kPlaneWords];    // X planes: ht[x*33+z] bit y = ey transposed
+    uint32_t mask[192 * kPad];
     uint32_t ey[kPlaneWords];    // ey[z*33+y] bit x = (id(x,y,z) == id(x,y-1,z))   (row y=0 unused)
     uint32_t ez[kPlaneWords];    // ez[z*33+y] bit x = (id(x,y,z) == id(x,y,z-1))   (layer z=0 unused)
-    uint32_t ht[kPlaneWords];    // X planes: ht[x*33+z] bit y = ey transposed
     uint32_t vt[kPlaneWords];    // X planes: vt[x*33+z] bit y = ez transposed
-    uint32_t mask[192 * kPad];
     uint32_t staging[kCap];
+    static constexpr int kArena = 3 * kPlaneWords + kCap;
 };
 
 template <bool kGreedy>
@@ -116,6 +121,9 @@ struct __align__(128) Smem {
     uint32_t actz[32];          // actz[z] bit y: row (y,z) carries at least one visible face
     uint32_t wred[kWarps][4];
     uint32_t scratch[kWarps + 1];
+    uint32_t seg[192];          // greedy: first log entry of each plane
+    uint32_t rows[192];         // greedy: visited rows of each plane
+    uint32_t first_run[192];    // greedy: ordinal of the first run of each plane
     uint32_t cursor;            // staging fill level
     uint32_t ones;              // 0xFFFFFFFF: stand-in equality row for single-id chunks
     unsigned long long first;
@@ -256,7 +264,6 @@ __device__ __forceinline__ bool load_halo(Smem<kGreedy>& sm, const uint16_t* __r
                 if (lane == 0) prof.count(15, (unsigned long long)(t + 1));
             }
             if (lane == 0) prof.count(have ? 12 : 13);
-            prof.mark(14);
         }
         if (!have) {                                      // gather from the neighbour's voxels: one u16 per 64-byte row
             const uint16_t* nv = voxels + (size_t)nb * VXP_CHUNK_VOXELS + (f ? 0 : 31) + 32 * lane;
@@ -426,16 +433,9 @@ __device__ __forceinline__ void sweep_emit(const Sweep& st, uint32_t dS, uint32_
 }
 
 
-// One row step (v in [0,32]); v == 32 flushes the runs still active after the last row.
-__device__ __forceinline__ void sweep_step(Sweep& st, int v, uint32_t* staging, uint32_t cap, uint32_t* cursor) {
-    if (v == 32) {
-        sweep_emit(st, st.S, st.E, 32, staging, cap, cursor);
-        st.S = st.E = st.C = 0;
-        return;
-    }
-    const uint32_t Mv = st.m[v];
-    if ((Mv | st.C) == 0) return;
-    const uint32_t Hv = st.hb[v * st.hs], Vv = st.vb[v * st.vs];
+// The row update proper.  Returns the dead runs (start / end bits) through dS / dE.
+__device__ __forceinline__ void sweep_row(Sweep& st, int v, uint32_t Mv, uint32_t Hv, uint32_t Vv, uint32_t& dS,
+                                          uint32_t& dE) {
     uint32_t Cs = 0;
     if (st.C) {
         const uint32_t X = st.C & Mv & Vv;
@@ -444,8 +444,9 @@ __device__ __forceinline__ void sweep_step(Sweep& st, int v, uint32_t* staging, 
         const uint32_t P = __brev(st.C) & ~__brev(st.S);
         const uint32_t Q = P + __brev(Es);
         Cs = __brev(Q ^ P);                                     // their cover
-        sweep_emit(st, st.S & ~Cs, st.E & ~Cs, v, staging, cap, cursor);
     }
+    dS = st.S & ~Cs;
+    dE = st.E & ~Cs;
     const uint32_t R = Mv & ~Cs;
     const uint32_t NS = R & ~((R << 1) & Hv);
     const uint32_t NE = R & ~((R >> 1) & (Hv >> 1));
@@ -457,6 +458,136 @@ __device__ __forceinline__ void sweep_step(Sweep& st, int v, uint32_t* staging, 
     st.r2 = (st.r2 & ~NS) | ((v & 4) ? NS : 0u);
     st.r3 = (st.r3 & ~NS) | ((v & 8) ? NS : 0u);
     st.r4 = (st.r4 & ~NS) | ((v & 16) ? NS : 0u);
+}
+
+// One row step (v in [0,32]); v == 32 flushes the runs still active after the last row.
+// (Used by the stepped heavy path; the normal path is sweep_plane below.)
+__device__ __forceinline__ void sweep_step(Sweep& st, int v, uint32_t* staging, uint32_t cap, uint32_t* cursor) {
+    if (v == 32) {
+        sweep_emit(st, st.S, st.E, 32, staging, cap, cursor);
+        st.S = st.E = st.C = 0;
+        return;
+    }
+    const uint32_t Mv = st.m[v];
+    if ((Mv | st.C) == 0) return;
+    uint32_t dS, dE;
+    const uint32_t r0 = st.r0, r1 = st.r1, r2 = st.r2, r3 = st.r3, r4 = st.r4;   // start rows before the update
+    Sweep old = st;
+    sweep_row(st, v, Mv, st.hb[v * st.hs], st.vb[v * st.vs], dS, dE);
+    old.r0 = r0; old.r1 = r1; old.r2 = r2; old.r3 = r3; old.r4 = r4;
+    sweep_emit(old, dS, dE, v, staging, cap, cursor);
+}
+
+// ---- the normal path.  Every instruction on the row recurrence costs its full latency (the
+// chain has no parallelism and a CTA has few other warps to hide it), so the sweep proper does the
+// bare minimum per row and everything else happens afterwards in parallel:
+//
+//   sweep_log    (one thread per plane, whole warps in lock step) visits only the rows that can
+//                change anything - row v matters iff mask row v or v-1 is non-empty - and logs, for
+//                each non-empty row, the cover Cs of the runs that survive into it, in the plane's
+//                private segment of the log.  No start rows, no atomics.
+//   stage_births (all threads, one log entry each) recomputes the runs that START at the entry's row
+//                (cells not covered by survivors, split at id changes) and stages one record per
+//                run, height still 1.
+//   run_height   (one thread per record, inside the flush) walks the following entries of the plane
+//                while the run's first column stays covered.
+struct SweepLog {
+    uint2* entry;          // [nL] .x = survivors' cover of a visited row, .y = plane<<5 | row | (runs started by the
+                           //      plane's earlier rows) << 13; plane segments back to back
+    const uint32_t* seg;   // [192] first entry of each plane
+    const uint32_t* rows;  // [192] non-empty (= logged) rows of each plane (bit mask)
+    const uint32_t* first; // [192] ordinal of the plane's first run
+};
+
+// Non-empty mask rows of the plane, as a bit mask.  The sweep visits rows rm | rm<<1 (a row matters iff it
+// or the row before it is non-empty; row 32 never needs a visit: what is alive after row 31 just ends
+// there) and logs the non-empty ones.
+__device__ __forceinline__ uint32_t sweep_rows(const Sweep& st) {
+    uint32_t rm = 0;
+#pragma unroll
+    for (int v = 0; v < 32; ++v) rm |= (uint32_t)(st.m[v] != 0) << v;
+    return rm;
+}
+
+// Returns the number of runs the plane starts (= its quads).
+__device__ __forceinline__ uint32_t sweep_log(Sweep& st, uint32_t rm, uint32_t plane, uint2* entry) {
+    uint32_t births = 0;
+    uint32_t todo = rm | (rm << 1);
+    bool valid = todo != 0;
+    int v = valid ? __ffs(todo) - 1 : 0;
+    todo &= todo - 1;
+    uint32_t Mv = st.m[v], Hv = st.hb[v * st.hs], Vv = st.vb[v * st.vs];
+    while (__any_sync(kFull, valid)) {
+        const bool validn = todo != 0;
+        const int vn = validn ? __ffs(todo) - 1 : 0;
+        todo &= todo - 1;
+        const uint32_t Mn = st.m[vn], Hn = st.hb[vn * st.hs], Vn = st.vb[vn * st.vs];
+        if (valid) {
+            uint32_t Cs = 0;
+            if (st.C) {
+                const uint32_t X = st.C & Mv & Vv;
+                const uint32_t T = (X & ~st.E) + st.S;
+                const uint32_t Es = T & st.E & X;                       // end bits of the surviving runs
+                const uint32_t P = __brev(st.C) & ~__brev(st.S);
+                Cs = __brev((P + __brev(Es)) ^ P);                      // their cover
+            }
+            const uint32_t R = Mv & ~Cs;
+            const uint32_t NS = R & ~((R << 1) & Hv);
+            st.S = (st.S & Cs) | NS;
+            st.E = (st.E & Cs) | (R & ~((R >> 1) & (Hv >> 1)));
+            st.C = Mv;
+            if (Mv) *entry++ = make_uint2(Cs, plane << 5 | (uint32_t)v | births << 13);
+            births += __popc(NS);
+        }
+        v = vn; valid = validn; Mv = Mn; Hv = Hn; Vv = Vn;
+    }
+    return births;
+}
+
+// H row (bit u: cell u has the id of cell u-1) of plane `plane`, row v.
+template <bool kGreedy>
+__device__ __forceinline__ uint32_t plane_h_row(const Smem<kGreedy>& sm, bool with_eq, uint32_t plane, uint32_t v) {
+    if constexpr (kGreedy) {
+        if (with_eq) {
+            const Post<true>& P = sm.tile.post;
+            const uint32_t f = plane >> 5, s = plane & 31u;
+            return f < 2 ? P.ht[s * kPad + v] : f < 4 ? P.ex[v * kPad + s] : P.ex[s * kPad + v];
+        }
+    }
+    return kFull;
+}
+
+// One record (u | v<<5 | s<<10 | f<<15 | (w-1)<<18, height 1) per run that starts at a logged row, at its
+// ordinal: the plane's first ordinal + the runs of the plane's earlier rows + its rank in the row.
+template <bool kGreedy>
+__device__ __forceinline__ void stage_births(const Smem<kGreedy>& sm, bool with_eq, const SweepLog& log, uint32_t nL,
+                                             uint32_t* rec) {
+    const uint32_t* mask = sm.tile.post.mask;
+    for (uint32_t i = threadIdx.x; i < nL; i += kThreads) {
+        const uint2 en = log.entry[i];
+        const uint32_t plane = (en.y >> 5) & 255u, v = en.y & 31u;
+        const uint32_t R = mask[plane * kPad + v] & ~en.x;           // cells of this row not covered from above
+        if (R == 0) continue;
+        const uint32_t Hv = plane_h_row(sm, with_eq, plane, v);
+        uint32_t NS = R & ~((R << 1) & Hv), NE = R & ~((R >> 1) & (Hv >> 1));
+        uint32_t pos = log.first[plane] + (en.y >> 13);
+        const uint32_t base = (en.y & 0x1FFFu) << 5;                  // f<<15 | s<<10 | v<<5
+        do {
+            const uint32_t u = __ffs(NS) - 1, e = __ffs(NE) - 1;
+            NS &= NS - 1;
+            NE &= NE - 1;
+            rec[pos++] = base | u | (e - u) << 18;
+        } while (NS);
+    }
+}
+// Height of the run of a staged record: rows v+1.. whose log entry keeps column u covered.
+__device__ __forceinline__ uint32_t run_height(const SweepLog& log, uint32_t rec) {
+    const uint32_t u = rec & 31u, v = (rec >> 5) & 31u, plane = (rec >> 10) & 255u;
+    const uint32_t rows = log.rows[plane];
+    const uint2* en = log.entry + log.seg[plane] + __popc(rows & ((1u << v) - 1u));   // the entry of row v
+    uint32_t h = 1;
+    while (v + h < 32u && ((rows >> (v + h)) & 1u) && ((en[h].x >> u) & 1u)) ++h;
+    return h;
 }
 
 // ------------------------------------------------------------------ staged records -> buffers
@@ -486,16 +617,15 @@ __device__ __forceinline__ void store_quad(unsigned long long* dst, uint32_t rec
 // The first batch of records and block ids is fetched before `before_first()` + the optional
 // barrier, so the latency of the range reservation (a contended global atomic) overlaps the
 // id gather instead of preceding it.  Returns false if the chunk does not fit the arena.
-template <bool kGreedy, class IdFn, class Pre>
-__device__ __forceinline__ bool flush_staging(Smem<kGreedy>& sm, uint32_t cnt, uint32_t ord0, const MeshOut& out, IdFn id_of,
-                                              Pre before_first, bool barrier) {
+template <bool kGreedy, class RecFn, class IdFn, class Pre>
+__device__ __forceinline__ bool flush_staging(Smem<kGreedy>& sm, RecFn rec_at, uint32_t cnt, uint32_t ord0, const MeshOut& out,
+                                              IdFn id_of, Pre before_first, bool barrier) {
     const int tid = threadIdx.x;
-    const uint32_t* staging = sm.tile.post.staging;
     uint32_t rec[4], b[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t i = tid + k * kThreads;
-        rec[k] = i < cnt ? staging[i] : 0u;
+        rec[k] = i < cnt ? rec_at(i) : 0u;
         b[k] = i < cnt ? id_of(rec_origin_voxel(rec[k])) : 0u;
     }
     before_first();
@@ -509,7 +639,7 @@ __device__ __forceinline__ bool flush_staging(Smem<kGreedy>& sm, uint32_t cnt, u
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t i = i0 + k * kThreads;
-                rec[k] = i < cnt ? staging[i] : 0u;
+                rec[k] = i < cnt ? rec_at(i) : 0u;
                 b[k] = i < cnt ? id_of(rec_origin_voxel(rec[k])) : 0u;
             }
         }
@@ -549,6 +679,7 @@ __device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bo
     uint32_t* const staging = sm.tile.post.staging;
     const uint32_t* const mask = sm.tile.post.mask;
     auto nothing = [] {};
+    auto staged = [staging](uint32_t i) { return staging[i]; };
     if constexpr (!kGreedy) {
         // ---- culled: every set bit is a quad.  Pass 1: thread t counts rows t, t+256, ... and lists the
         // non-empty ones; pass 2: the threads share that list evenly, so the work is balanced however
@@ -592,50 +723,90 @@ __device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bo
             __syncthreads();
             prof.mark(6);
             bool fits;
-            if (base == 0) fits = flush_staging(sm, end, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); }, true);
-            else fits = flush_staging(sm, end - base, base, out, id_of, nothing, false);
+            if (base == 0) fits = flush_staging(sm, staged, end, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); }, true);
+            else fits = flush_staging(sm, staged, end - base, base, out, id_of, nothing, false);
             if (!fits) return;
             __syncthreads();
             prof.mark(7);
         }
         return;
     } else {
-        // ---- greedy: optimistic single sweep with everything staged
+        // ---- greedy: sweep_log, stage_births, run_height (see above).  The log sits at the end of the
+        // staging area; the records go below it if they fit (the V arrays then stay intact for the stepped
+        // fallback) and otherwise, the sweep being over, from ey up.
+        Post<true>& P = sm.tile.post;
         if (tid == 0) sm.cursor = 0;
-        __syncthreads();
         Sweep st;
         sweep_init(st, sm, with_eq);
-        if (tid < 192) {
-#pragma unroll 1
-            for (int v = 0; v <= 32; ++v) sweep_step(st, v, staging, kCap, &sm.cursor);
-        }
-        __syncthreads();
-        prof.mark(5);
-        const uint32_t Q = sm.cursor;
+        const uint32_t rm = tid < 192 ? sweep_rows(st) : 0u;
+        uint32_t nL;
+        const uint32_t seg = block_excl_scan((uint32_t)__popc(rm), sm.scratch, &nL);   // barriers: cursor = 0 published
+        if (tid < 192) { sm.seg[tid] = seg; sm.rows[tid] = rm; }
+        const bool log_fits = 2 * nL <= kCap;
+        SweepLog log;
+        log.entry = reinterpret_cast<uint2*>(staging + kCap - 2 * nL);
+        log.seg = sm.seg;
+        log.rows = sm.rows;
+        log.first = sm.first_run;
+        uint32_t Q = 0;
         unsigned long long f = 0;
-        if (tid == 0) f = atomicAdd(out.total, (unsigned long long)Q);
-        auto publish = [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); };
-        if (Q <= kCap) {
-            flush_staging(sm, Q, 0, out, id_of, publish, true);
-            prof.mark(7);
-            return;
+        if (log_fits) {
+            uint32_t births = 0;
+#ifdef VXP_PROFILE
+            const long long t_sw = clock64();
+#endif
+            if (tid < 192) births = sweep_log(st, rm, (uint32_t)tid, log.entry + seg);   // warps 0..5, whole warps
+#ifdef VXP_PROFILE
+            if ((tid & 31) == 0 && blockIdx.x < kProfCtas) g_prof_warp[blockIdx.x][tid >> 5] = (unsigned int)(clock64() - t_sw);
+#endif
+            const uint32_t first_run = block_excl_scan(births, sm.scratch, &Q);   // barriers: log published
+            if (tid < 192) sm.first_run[tid] = first_run;
+            if (tid == 0) f = atomicAdd(out.total, (unsigned long long)Q);       // in flight while the records are staged
+            prof.mark(5);
+            const uint32_t cap_small = kCap - 2 * nL, cap_arena = Post<true>::kArena - 2 * nL;
+            if (Q <= cap_arena) {                         // block-uniform
+                uint32_t* const rec = Q <= cap_small ? staging : P.ey;
+                __syncthreads();                          // first_run published; V arrays dead
+                stage_births(sm, with_eq, log, nL, rec);
+                __syncthreads();
+                prof.mark(6);
+                flush_staging(sm, [rec, &log](uint32_t i) { const uint32_t r = rec[i]; return r | (run_height(log, r) - 1u) << 23; },
+                              Q, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); }, true);
+                prof.mark(7);
+                return;
+            }
+        } else {
+            // the log alone does not fit: count with a cursor-only stepped sweep
+            if (tid < 192) {
+#pragma unroll 1
+                for (int v = 0; v <= 32; ++v) sweep_step(st, v, staging, 0u, &sm.cursor);
+            }
+            __syncthreads();
+            Q = sm.cursor;
+            if (tid == 0) f = atomicAdd(out.total, (unsigned long long)Q);
         }
-        // heavy path (Q > kCap): sweep again, half of the planes per step (<= 96*32 quads), flushing each time
+        auto publish = [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); };
+        prof.count(14);
+        // heavy path (the log or the records do not fit): sweep again row by row, half of the planes per
+        // step (<= 96*32 quads), staging through a cursor and flushing whenever the next step might not fit
         publish();
         sweep_init(st, sm, with_eq);
         uint32_t flushed = 0;
+        if (tid == 0) sm.cursor = 0;
 #pragma unroll 1
         for (int v = 0; v <= 32; ++v) {
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
-                __syncthreads();
-                if (tid == 0) sm.cursor = 0;
-                __syncthreads();
+                __syncthreads();                          // cursor reset / previous flush done
                 if (tid < 192 && (tid >= 96) == (half == 1)) sweep_step(st, v, staging, kCap, &sm.cursor);
                 __syncthreads();
                 const uint32_t cnt = sm.cursor;
-                if (!flush_staging(sm, cnt, flushed, out, id_of, nothing, false)) return;
-                flushed += cnt;
+                if (cnt + 96 * 32 > kCap || (v == 32 && half == 1)) {   // the next half step might not fit
+                    if (!flush_staging(sm, staged, cnt, flushed, out, id_of, nothing, false)) return;
+                    flushed += cnt;
+                    __syncthreads();
+                    if (tid == 0) sm.cursor = 0;
+                }
             }
         }
         prof.mark(7);
