@@ -45,47 +45,69 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled (NVML, in-process, every 50 ms) while the GPU is under load.
+    NVML is initialised before the warm-up so its start-up cost never lands in the timed region."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.t = index, [], None, None
+        self.index, self.rows, self.t, self.stop_flag, self.h, self.nv = index, [], None, False, None, None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+            except Exception:
+                pass
+            try:
+                self.h = nv.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid) if uuid else None
+            except Exception:
+                self.h = None
+            if self.h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+                self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = nv
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        if self.nv is None:
             return
-        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.rows.append((time.time(), float(mhz), int(reasons), int(util)))
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def stop(self, t0: float, t1: float, window: str):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "window": "nvidia-smi unavailable"}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 9]
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "window": "NVML unavailable"}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        nv = self.nv
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
         if not rows:
-            rows, window = [r for (_, r) in self.rows if len(r) >= 9], "whole run (timed region shorter than one sample)"
-        busy = [r for r in rows if r[4].isdigit() and int(r[4]) > 0] or rows
-        sm = [float(r[1]) for r in busy if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in busy if r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[5 + k].lower().startswith("active") for r in busy)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(busy), "window": window}
+            rows, window = [r for r in self.rows if r[3] > 0] or self.rows, "whole run under load (timed region shorter than one sample)"
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = [n for n, b in bits.items() if any(r[2] & b for r in rows)]
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(rows), "window": window}
 
 
 def workload_coords(workload: str, rank: int, world: int):
@@ -120,8 +142,14 @@ def run_reference(args):
         sample = "256 checkerboard chunks (z-layer 0 of the 16^3 block) per step"
         batches = [(vox, nbr_s)]
     else:
-        batches = [(O.terrain_fill_batch(42 + k, coords, threads), nbr) for k in range(2)]
-        sample = "the full 4096-chunk batch per step (seeds 42,43 alternating)"
+        # bounded sample so that any --steps the driver passes ends within minutes: the first 1024 chunks
+        # (z-layers 0..3 of the 16^3 block: every height band, so the air / buried / surface mix is the batch's)
+        n_ref = 1024
+        sub = coords[:n_ref]
+        nbr_s = nbr[:n_ref].copy()
+        nbr_s[nbr_s >= n_ref] = -1
+        batches = [(O.terrain_fill_batch(42 + k, sub, threads), nbr_s) for k in range(2)]
+        sample = "first 1024 chunks (z-layers 0..3) of the 4096-chunk batch per step, seeds 42,43 alternating"
     cap = int(max(O.mesh_batch_hash(v, n, mode, threads)[1].sum() for v, n in batches))
     times = []
     for s in range(args.warmup + args.steps):
@@ -149,8 +177,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--workload", default="terrain_culled",
                     choices=["terrain_culled", "terrain_greedy", "checker_culled", "checker_greedy", "world_fused"])
     ap.add_argument("--impl", default="vxp", choices=["vxp", "reference"])
@@ -278,8 +306,11 @@ def main():
     mean_bytes = statistics.mean(alg_bytes[s % len(batches)] for s in range(args.steps))
     peak, peak_src = hbm_peak()
     achieved = mean_bytes / (mean_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+    # (profiles/r1_ncu_*_summary.txt); None for workloads that were not captured
+    ncu_traffic = {"terrain_culled": 273.4e6 + 75.8e6, "terrain_greedy": 278.9e6 + 28.1e6}.get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "mesh_kernel" if not fused else "terrain_mesh_kernel",
+                "traffic": ncu_traffic, "peak_source": peak_src, "kernel": "mesh_kernel" if not fused else "terrain_mesh_kernel",
                 "kernel_ms_mean": mean_ms, "kernel_ms_min": min(kernel_ms),
                 "algorithmic_bytes_per_launch": mean_bytes,
                 "note": "event bracket = 8-byte counter memset + kernel"}

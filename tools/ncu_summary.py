@@ -1,0 +1,53 @@
+"""Condense ncu exports into the small text files kept under profiles/.
+
+  python tools/ncu_summary.py launches <launches.csv> <out.csv>       # per-launch durations + per-kernel share
+  python tools/ncu_summary.py kernel <raw.csv> <source.csv> <out.txt>  # key counters + hottest source lines
+(raw.csv: `ncu -i X.ncu-rep --page raw --csv`; source.csv: `--page source --print-source cuda,sass --csv`)
+"""
+import csv, subprocess, sys, collections
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__cycles_elapsed.avg", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
+        "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor", "launch__grid_size", "launch__block_size",
+        "launch__shared_mem_per_block_dynamic", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+
+
+def launches(src, dst):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
+    out = [("id", "kernel", "grid", "block", "duration_us")]
+    per = collections.OrderedDict()
+    for r in rows:
+        name = r[4].split("(")[0].replace("void ", "")
+        val = float(r[-1].replace(",", "")) / (1e3 if r[-2] in ("ns", "nsecond") else 1.0)
+        out.append((r[0], name, r[8], r[7], f"{val:.3f}"))
+        per.setdefault(name, []).append(val)
+    tot = sum(sum(v) for v in per.values())
+    with open(dst, "w") as f:
+        w = csv.writer(f)
+        w.writerows(out)
+        f.write("\n# per-kernel share of the profiled launches (cold-cache, serialised: compare shares, not absolutes)\n")
+        for k, v in per.items():
+            f.write(f"# {k}: n={len(v)} mean={sum(v)/len(v):.2f} us share={100*sum(v)/tot:.1f}%\n")
+
+
+def kernel(raw, source, dst):
+    rows = list(csv.reader(open(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    with open(dst, "w") as f:
+        for n, r in enumerate(data):
+            f.write(f"== launch {n}: {r[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else ''}\n")
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write(f"   {k:70s} {r[i]} {units[i]}\n")
+        f.write("\n== hottest CUDA source lines (warp-stall samples, instructions executed)\n")
+        f.write(subprocess.run([sys.executable, __file__.replace("ncu_summary.py", "ncu_lines.py"), source, "32"],
+                               capture_output=True, text=True).stdout)
+
+
+if __name__ == "__main__":
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](*sys.argv[2:])
