@@ -69,8 +69,20 @@ class ClockSampler:
                 self.h = nv.nvmlDeviceGetHandleByIndex(phys)
             self.nv = nv
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            # the first call of each NVML query takes milliseconds (measured: 11.6 ms / 4.4 ms, later ones
+            # ~1 us) and holds driver locks the launch path needs: pay that here, not in the timed region
+            for _ in range(2):
+                nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                self._reasons()
+                nv.nvmlDeviceGetUtilizationRates(self.h)
         except Exception:
             self.nv = None
+
+    def _reasons(self):
+        nv = self.nv
+        if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons"):
+            return nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        return nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
 
     def start(self):
         if self.nv is None:
@@ -83,8 +95,7 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
-                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                reasons = self._reasons()
                 util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
                 self.rows.append((time.time(), float(mhz), int(reasons), int(util)))
             except Exception:

@@ -1,6 +1,7 @@
 #!/bin/bash
 # quick A/B of mesh-kernel variants on the config-2/3 batch: prints culled / greedy ms per step per library
 for lib in "$@"; do
+  VXP_LIB=$PWD/voxelphile_b200/$lib python -c "from voxelphile_b200 import Mesher,_lib; m=Mesher(0); l=_lib.load(); print('$lib', 'smem culled/greedy', l.vxp_debug_smem_bytes(0), l.vxp_debug_smem_bytes(1), 'CTAs/SM stored c/g', l.vxp_debug_occupancy(0,0), l.vxp_debug_occupancy(1,0), 'fused c/g', l.vxp_debug_occupancy(0,1), l.vxp_debug_occupancy(1,1))"
   VXP_LIB=$PWD/voxelphile_b200/$lib timeout -k 10 200 python bench.py --no-cpu --e2e-steps 0 --steps 200 > gpurun_out/qb_$lib.json 2>/dev/null
   python - "$lib" <<'PY'
 import json,sys

@@ -233,6 +233,20 @@ cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_
 size_t boundary_tag_bytes(uint32_t n) { return (size_t)n * sizeof(uint32_t); }
 size_t boundary_plane_bytes(uint32_t n) { return (size_t)n * 64 * sizeof(unsigned long long); }
 
+// diagnostics (not part of include/vxp.h): resident CTAs per SM of a mesh kernel on the current device
+extern "C" int vxp_debug_occupancy(int greedy, int fused) {
+    int n = -1;
+    cudaError_t e;
+    if (fused)
+        e = greedy ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, terrain_mesh_kernel<true>, kThreads, sizeof(v4::Smem<true>))
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, terrain_mesh_kernel<false>, kThreads, sizeof(v4::Smem<false>));
+    else
+        e = greedy ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v4::mesh_kernel<true>, kThreads, sizeof(v4::Smem<true>))
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v4::mesh_kernel<false>, kThreads, sizeof(v4::Smem<false>));
+    return e == cudaSuccess ? n : -1;
+}
+extern "C" int vxp_debug_smem_bytes(int greedy) { return greedy ? (int)sizeof(v4::Smem<true>) : (int)sizeof(v4::Smem<false>); }
+
 #ifdef VXP_PROFILE
 extern "C" int vxp_debug_read_prof_warp(unsigned int* out, int max_ctas) {
     const int ctas = max_ctas < v4::kProfCtas ? max_ctas : v4::kProfCtas;
