@@ -182,6 +182,52 @@ __device__ __forceinline__ int terrain_height(const TerrainKeys& tk, int X, int 
     }
     return 256 + (int)(sum >> 40);
 }
+// ---- the same height function with the lattice gradients of a chunk's footprint hashed once.
+// A footprint of at most 34 columns per axis touches at most 5 lattice points per axis in every
+// octave (cells are 128, 64, 32, 16 wide), so 4 x 5 x 5 = 100 gradient hashes serve all of its
+// columns; per column only the interpolation is left.  Bit-exact with terrain_height().
+struct TerrainLattice {
+    int ix0[4], iz0[4];          // lattice index of the footprint origin, per octave
+    short g[4][5][5];            // gradient of lattice point (ix0+i, iz0+j): gx in the low byte, gz in the high byte
+};
+// threads 0..99 of the CTA; X0, Z0 = world coordinates of the footprint origin; needs a barrier afterwards
+__device__ __forceinline__ void terrain_lattice_fill(TerrainLattice& L, const TerrainKeys& tk, int X0, int Z0) {
+    const int t = threadIdx.x;
+    if (t >= 100) return;
+    const int o = t / 25, r = t - 25 * o, i = r / 5, j = r - 5 * i;
+    const int S = 7 - o;
+    const int ix0 = (X0 + 37 * o) >> S, iz0 = (Z0 + 59 * o) >> S;
+    const uint32_t g = mix32(mix32(tk.k[o] + (uint32_t)(ix0 + i) * 0x85EBCA6Bu) ^ ((uint32_t)(iz0 + j) * 0xC2B2AE35u)) & 7u;
+    const int gx = (g < 4) ? ((g < 2) ? (g == 0 ? 1 : -1) : 0) : ((g & 1) ? -1 : 1);
+    const int gz = (g < 4) ? ((g < 2) ? 0 : (g == 2 ? 1 : -1)) : ((g & 2) ? -1 : 1);
+    L.g[o][i][j] = (short)((gx & 0xFF) | (gz << 8));
+    if (r == 0) { L.ix0[o] = ix0; L.iz0[o] = iz0; }
+}
+__device__ __forceinline__ int lattice_dot(short g, int ax, int az) {
+    return (int)(signed char)(g & 0xFF) * ax + (int)(g >> 8) * az;
+}
+__device__ __forceinline__ int terrain_height_lattice(const TerrainLattice& L, int X, int Z) {
+    long long sum = 0;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const int S = 7 - o;
+        const int A = 192 >> o;
+        const int Xo = X + 37 * o, Zo = Z + 59 * o;
+        const int i = (Xo >> S) - L.ix0[o], j = (Zo >> S) - L.iz0[o];
+        const int dx = (Xo & ((1 << S) - 1)) << (8 - S);
+        const int dz = (Zo & ((1 << S) - 1)) << (8 - S);
+        const int d00 = lattice_dot(L.g[o][i][j], dx, dz);
+        const int d10 = lattice_dot(L.g[o][i + 1][j], dx - 256, dz);
+        const int d01 = lattice_dot(L.g[o][i][j + 1], dx, dz - 256);
+        const int d11 = lattice_dot(L.g[o][i + 1][j + 1], dx - 256, dz - 256);
+        const int fx = fade16(dx), fz = fade16(dz);
+        const int n0 = d00 * 65536 + fx * (d10 - d00);
+        const int n1 = d01 * 65536 + fx * (d11 - d01);
+        const long long n = (long long)n0 * 65536 + (long long)fz * (long long)(n1 - n0);
+        sum += n * A;
+    }
+    return 256 + (int)(sum >> 40);
+}
 __device__ __forceinline__ uint32_t terrain_block(int h, int Y) {
     if (Y > h) return 0u;
     if (Y == h) return 1u;

@@ -11,58 +11,49 @@
 namespace vxp {
 
 // ====================================================================== terrain fill (SPEC §6)
-// One CTA per chunk: 1024 column heights -> shared memory, then 4096 16-byte stores.
+// One CTA per chunk: lattice gradients of the footprint (100 hashes), 1024 column heights -> shared
+// memory, then 4096 16-byte stores.  Rows entirely above the surface of their z-layer, or entirely
+// below its dirt, skip the per-voxel classification.
 __global__ void __launch_bounds__(kThreads) terrain_fill_kernel(const vxp_coord* __restrict__ coords, uint32_t n,
                                                                  uint64_t seed, uint16_t* __restrict__ out) {
-    __shared__ int s_h[1024];
-    __shared__ int s_red[2 * kWarps];
+    __shared__ TerrainLattice s_lat;
+    __shared__ short s_h[1024];
+    __shared__ short s_zmin[32], s_zmax[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TerrainKeys tk = terrain_keys(seed);
     for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         const vxp_coord c = coords[chunk];
-        int hmin = INT_MAX, hmax = INT_MIN;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int col = tid + k * kThreads; // col = z*32 + x
-            const int h = terrain_height(tk, 32 * c.x + (col & 31), 32 * c.z + (col >> 5));
-            s_h[col] = h;
-            hmin = min(hmin, h);
-            hmax = max(hmax, h);
-        }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            hmin = min(hmin, __shfl_xor_sync(kFull, hmin, d));
-            hmax = max(hmax, __shfl_xor_sync(kFull, hmax, d));
-        }
-        if (lane == 0) { s_red[warp] = hmin; s_red[kWarps + warp] = hmax; }
+        terrain_lattice_fill(s_lat, tk, 32 * c.x, 32 * c.z);
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kWarps + w]); }
+        for (int k = 0; k < 4; ++k) {
+            const int z = warp + k * kWarps;                 // a warp owns the 32 columns of one z-layer
+            const int h = terrain_height_lattice(s_lat, 32 * c.x + lane, 32 * c.z + z);
+            s_h[z * 32 + lane] = (short)h;
+            const int lo = __reduce_min_sync(kFull, h), hi = __reduce_max_sync(kFull, h);
+            if (lane == 0) { s_zmin[z] = (short)lo; s_zmax[z] = (short)hi; }
+        }
+        __syncthreads();
 
         uint4* dst = reinterpret_cast<uint4*>(out + (size_t)chunk * VXP_CHUNK_VOXELS);
         const int Y0 = 32 * c.y;
-        if (Y0 > hmax) {                       // whole chunk above the surface: air
 #pragma unroll 4
-            for (int j = tid; j < 4096; j += kThreads) dst[j] = make_uint4(0, 0, 0, 0);
-        } else if (Y0 + 31 < hmin - 3) {       // whole chunk below the dirt: stone/slate bands by Y only
-#pragma unroll 4
-            for (int j = tid; j < 4096; j += kThreads) {
-                const int Y = Y0 + ((j >> 2) & 31);
-                const uint32_t b = ((Y >> 3) & 1) ? 4u : 3u;
-                const uint32_t bb = b | b << 16;
-                dst[j] = make_uint4(bb, bb, bb, bb);
-            }
-        } else {
-#pragma unroll 2
-            for (int j = tid; j < 4096; j += kThreads) { // j = (z*32 + y)*4 + p
-                const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
-                const int* hp = s_h + z * 32 + x0;
+        for (int j = tid; j < 4096; j += kThreads) {         // j = (z*32 + y)*4 + p
+            const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
+            uint4 v;
+            if (Y > s_zmax[z]) {                             // above every column of this layer: air
+                v = make_uint4(0, 0, 0, 0);
+            } else if (Y < s_zmin[z] - 3) {                  // below the dirt of every column: stone / slate by Y only
+                const uint32_t b = ((Y >> 3) & 1) ? 4u : 3u, bb = b | b << 16;
+                v = make_uint4(bb, bb, bb, bb);
+            } else {
+                const short* hp = s_h + z * 32 + x0;
                 uint32_t w[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
-                dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
+                v = make_uint4(w[0], w[1], w[2], w[3]);
             }
+            dst[j] = v;
         }
         __syncthreads();
     }
@@ -99,6 +90,7 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t s
     v4::Smem<kGreedy>& sm = *reinterpret_cast<v4::Smem<kGreedy>*>(smem_raw);
     __shared__ short s_h[34 * 34];   // heights of the column footprint: s_h[(z+1)*34 + (x+1)]  (|h-256| <= 720)
     __shared__ int s_red[2 * kWarps];
+    __shared__ TerrainLattice s_lat;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t chunk = blockIdx.x;
     if (chunk >= n) return;
@@ -107,6 +99,8 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t s
     v4::Prof prof;
     prof.start(tid == 0);
     if (tid == 0) sm.ones = kFull;
+    terrain_lattice_fill(s_lat, tk, 32 * c.x - 1, 32 * c.z - 1);
+    __syncthreads();
 
     int hmin = INT_MAX, hmax = INT_MIN;
     for (int i = tid; i < 34 * 34; i += kThreads) {
@@ -114,7 +108,7 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t s
         const bool corner = (zz < 0 || zz > 31) && (xx < 0 || xx > 31);
         int h = 0;
         if (!corner) {
-            h = terrain_height(tk, 32 * c.x + xx, 32 * c.z + zz);
+            h = terrain_height_lattice(s_lat, 32 * c.x + xx, 32 * c.z + zz);
             hmin = min(hmin, h);
             hmax = max(hmax, h);
         }

@@ -88,10 +88,9 @@ template <bool kGreedy>
 struct Post;   // what lives in the tile's 64 KiB once the tile is dead
 template <>
 struct Post<false> {
-    static constexpr int kCap = (kTileBytes - 192 * kPad * 4) / 4 - 192 * 32 - kThreads;   // 3648 staged quad records
-    uint32_t mask[192 * kPad];   // mask[(f*32+s)*33 + v] bit u: face f of cell (u,v) in slice s visible
-    uint32_t rows[192 * 32];     // non-empty mask rows: row | (ordinal of its first quad inside its thread's share) << 13
-    uint32_t tbase[kThreads];    // ordinal of the first quad of each thread's share
+    static constexpr int kWords = 6 * 32 * 32;                             // face words of a chunk
+    static constexpr int kCap = (kTileBytes - kWords * 8) / 4;             // 4096 staged quad records
+    uint2 words[kWords];         // non-empty face words: .x = f<<10 | y<<5 | z | (ordinal of the word's first quad) << 13, .y = bits over x
     uint32_t staging[kCap];
 };
 template <>
@@ -153,11 +152,10 @@ struct ChunkFlags {
 };
 
 // ------------------------------------------------------------------ tile -> occupancy
-// Convert slab s (layers 8s..8s+7); accumulates the per-thread flag words.
-template <bool kGreedy>
-__device__ __forceinline__ void convert_slab(Smem<kGreedy>& sm, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and) {
+// Convert slab s (layers 8s..8s+7, 16 KiB at `slab`) into sm.occ; accumulates the per-thread flag words.
+template <class SM>
+__device__ __forceinline__ void convert_rows(SM& sm, const uint4* slab, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and) {
     const int tid = threadIdx.x;
-    const uint4* slab = reinterpret_cast<const uint4*>(sm.tile.vox) + s * (kSlabBytes / 16);
     unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -171,9 +169,13 @@ __device__ __forceinline__ void convert_slab(Smem<kGreedy>& sm, int s, uint32_t&
         occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)bits;
     }
 }
-// Block-wide flags; contains the barrier that publishes the occupancy interior.
 template <bool kGreedy>
-__device__ __forceinline__ ChunkFlags reduce_flags(Smem<kGreedy>& sm, uint32_t v_or, uint32_t v_and, uint32_t o_and) {
+__device__ __forceinline__ void convert_slab(Smem<kGreedy>& sm, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and) {
+    convert_rows(sm, reinterpret_cast<const uint4*>(sm.tile.vox) + s * (kSlabBytes / 16), s, v_or, v_and, o_and);
+}
+// Block-wide flags; contains the barrier that publishes the occupancy interior.
+template <class SM>
+__device__ __forceinline__ ChunkFlags reduce_flags(SM& sm, uint32_t v_or, uint32_t v_and, uint32_t o_and) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v_or = __reduce_or_sync(kFull, v_or);
     v_and = __reduce_and_sync(kFull, v_and);
@@ -210,8 +212,8 @@ __device__ __forceinline__ void issue_yz_halo(HaloRows& h, const uint16_t* __res
 // context scratch as self-validating 64-bit words (launch epoch in the high half), so readers
 // need no ordering and a single round trip; chunks that are all air / all solid publish one
 // tag word instead.
-template <bool kGreedy>
-__device__ __forceinline__ void publish_boundary(const Smem<kGreedy>& sm, const Bnd& bnd, uint32_t chunk, ChunkFlags fl) {
+template <class SM>
+__device__ __forceinline__ void publish_boundary(const SM& sm, const Bnd& bnd, uint32_t chunk, ChunkFlags fl) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!fl.any_solid || fl.all_solid) {
         if (tid == kThreads - 32) st_relaxed_u32(bnd.tags + chunk, bnd.epoch << 2 | (fl.any_solid ? kTagSolid : kTagAir));
@@ -235,8 +237,8 @@ __device__ __forceinline__ void publish_boundary(const Smem<kGreedy>& sm, const 
 // thread) whether any halo bit this thread produced is air.  Contains no barrier.
 // nb = neighbour index of face f = warp index (loaded by the caller before the tile wait).
 constexpr int kPlanePolls = 3;   // bounded re-reads of a boundary plane that is not there yet (never a wait-for)
-template <bool kGreedy>
-__device__ __forceinline__ bool load_halo(Smem<kGreedy>& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n,
+template <class SM>
+__device__ __forceinline__ bool load_halo(SM& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n,
                                           const Bnd& bnd, const HaloRows& rows, Prof& prof) {
     const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
     if (f >= 6) return false;
@@ -617,8 +619,8 @@ __device__ __forceinline__ void store_quad(unsigned long long* dst, uint32_t rec
 // The first batch of records and block ids is fetched before `before_first()` + the optional
 // barrier, so the latency of the range reservation (a contended global atomic) overlaps the
 // id gather instead of preceding it.  Returns false if the chunk does not fit the arena.
-template <bool kGreedy, class RecFn, class IdFn, class Pre>
-__device__ __forceinline__ bool flush_staging(Smem<kGreedy>& sm, RecFn rec_at, uint32_t cnt, uint32_t ord0, const MeshOut& out,
+template <class SM, class RecFn, class IdFn, class Pre>
+__device__ __forceinline__ bool flush_staging(SM& sm, RecFn rec_at, uint32_t cnt, uint32_t ord0, const MeshOut& out,
                                               IdFn id_of, Pre before_first, bool barrier) {
     const int tid = threadIdx.x;
     uint32_t rec[4], b[4];
@@ -662,12 +664,27 @@ __device__ __forceinline__ bool flush_staging(Smem<kGreedy>& sm, RecFn rec_at, u
 }
 
 // Thread 0: turn the result of the range reservation into sm.first and the chunk's meta entry.
-template <bool kGreedy>
-__device__ __forceinline__ void publish_range(Smem<kGreedy>& sm, uint32_t chunk, uint32_t Q, unsigned long long f,
+template <class SM>
+__device__ __forceinline__ void publish_range(SM& sm, uint32_t chunk, uint32_t Q, unsigned long long f,
                                               const MeshOut& out) {
     const bool fits = f + Q <= out.cap;
     out.meta[chunk] = vxp_chunk_meta{fits ? (uint32_t)f : 0xFFFFFFFFu, Q};
     sm.first = fits ? f : ~0ull;
+}
+
+// Face word (f, y, z): bit x = face f of voxel (x,y,z) visible.  f is a compile-time constant at every call site.
+template <class SM>
+__device__ __forceinline__ uint32_t face_word(const SM& sm, int f, int y, int z) {
+    const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
+    const uint32_t c = o[0];
+    switch (f) {
+        case 0: return c & ~((c << 1) | ((sm.xh[0][z] >> y) & 1u));
+        case 1: return c & ~((c >> 1) | ((sm.xh[1][z] >> y) & 1u) << 31);
+        case 2: return c & ~o[-1];
+        case 3: return c & ~o[+1];
+        case 4: return c & ~o[-34];
+        default: return c & ~o[+34];
+    }
 }
 
 // ------------------------------------------------------------------ masks -> quads -> buffers
@@ -677,53 +694,72 @@ __device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bo
     const int tid = threadIdx.x;
     constexpr uint32_t kCap = Post<kGreedy>::kCap;
     uint32_t* const staging = sm.tile.post.staging;
-    const uint32_t* const mask = sm.tile.post.mask;
     auto nothing = [] {};
     auto staged = [staging](uint32_t i) { return staging[i]; };
     if constexpr (!kGreedy) {
-        // ---- culled: every set bit is a quad.  Pass 1: thread t counts rows t, t+256, ... and lists the
-        // non-empty ones; pass 2: the threads share that list evenly, so the work is balanced however
-        // unevenly the faces are spread over the planes.
+        // ---- culled: every visible face is a quad.  No mask arrays, no transposes: thread (warp w, lane z) owns
+        // the 24 face words {(f, y, z) : (y + f) % 8 == w} (bit x = face f of voxel (x,y,z) visible) and derives
+        // them from the occupancy.  Pass 1 counts quads and non-empty words (one packed block scan gives every
+        // thread its first ordinal and its slot in the word list); pass 2 writes the non-empty words with the
+        // ordinal of their first quad; pass 3 shares the list evenly between the threads.
         Post<false>& P = sm.tile.post;
-        if (tid == 0) sm.cursor = 0;
-        __syncthreads();
-        uint32_t mine = 0;
-#pragma unroll 4
-        for (int r = tid; r < 192 * 32; r += kThreads) {
-            const uint32_t c = __popc(mask[(r >> 5) * kPad + (r & 31)]);
-            if (c) P.rows[atomicAdd(&sm.cursor, 1u)] = (uint32_t)r | mine << 13;
-            mine += c;
+        const int z = tid & 31, w = tid >> 5;
+        uint32_t packed = 0;                                   // quads | non-empty words << 17
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t word = face_word(sm, f, ((w - f) & 7) + 8 * j, z);
+                packed += (uint32_t)__popc(word) + (word ? 1u << 17 : 0u);
+            }
         }
-        uint32_t Q;
-        P.tbase[tid] = block_excl_scan(mine, sm.scratch, &Q);   // the scan's barriers also publish rows / cursor
+        uint32_t tot;
+        const uint32_t pre = block_excl_scan(packed, sm.scratch, &tot);
+        const uint32_t Q = tot & 0x1FFFFu, nwords = tot >> 17;
         if (Q == 0) {
             if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+            prof.count(10);
             return;
         }
-        unsigned long long f = 0;
-        if (tid == 0) f = atomicAdd(out.total, (unsigned long long)Q);   // in flight while the records are staged
+        prof.count(11);
+        unsigned long long fq = 0;
+        if (tid == 0) fq = atomicAdd(out.total, (unsigned long long)Q);   // in flight while the records are staged
+        {
+            uint32_t ord = pre & 0x1FFFFu, slot = pre >> 17;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int y = ((w - f) & 7) + 8 * j;
+                    const uint32_t word = face_word(sm, f, y, z);
+                    if (word) P.words[slot++] = make_uint2((uint32_t)(f << 10 | y << 5 | z) | ord << 13, word);
+                    ord += __popc(word);
+                }
+            }
+        }
         __syncthreads();
         prof.mark(5);
-        const uint32_t nrows = sm.cursor;
         for (uint32_t base = 0; base < Q; base += kCap) {
             const uint32_t end = min(Q, base + kCap);
-            for (uint32_t i = tid; i < nrows; i += kThreads) {     // neighbours in the list are rows of similar density
-                const uint32_t d = P.rows[i], r = d & 8191u;
-                uint32_t bits = mask[(r >> 5) * kPad + (r & 31)];
-                uint32_t o = P.tbase[r & (kThreads - 1)] + (d >> 13);
-                const uint32_t rbase = (r >> 5) << 10 | (r & 31u) << 5;   // f<<15|s<<10|v<<5
+            for (uint32_t i = tid; i < nwords; i += kThreads) {     // neighbours in the list are words of similar density
+                const uint2 d = P.words[i];
+                uint32_t bits = d.y, o = d.x >> 13;
                 if (o + __popc(bits) <= base || o >= end) continue;
+                const uint32_t f = (d.x >> 10) & 7u, y = (d.x >> 5) & 31u, zz = d.x & 31u;
+                // u | v<<5 | s<<10 | f<<15:  X planes (s,u,v) = (x,y,z);  Y planes (y,x,z);  Z planes (z,x,y)
+                const uint32_t rb = f << 15 | (f < 2 ? (y | zz << 5) : f < 4 ? (zz << 5 | y << 10) : (y << 5 | zz << 10));
+                const uint32_t sh = f < 2 ? 10u : 0u;
                 while (bits) {
-                    const int u = __ffs(bits) - 1;
+                    const uint32_t x = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    if (o >= base && o < end) staging[o - base] = rbase | (uint32_t)u;
+                    if (o >= base && o < end) staging[o - base] = rb | x << sh;
                     ++o;
                 }
             }
             __syncthreads();
             prof.mark(6);
             bool fits;
-            if (base == 0) fits = flush_staging(sm, staged, end, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); }, true);
+            if (base == 0) fits = flush_staging(sm, staged, end, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, chunk, Q, fq, out); }, true);
             else fits = flush_staging(sm, staged, end - base, base, out, id_of, nothing, false);
             if (!fits) return;
             __syncthreads();
@@ -832,16 +868,18 @@ __device__ __forceinline__ void mesh_tail(Smem<kGreedy>& sm, uint32_t chunk, Chu
             equality_store(sm.tile.post, res);
         }
     }
-    __syncthreads();
-    prof.mark(3);
-    const bool any = __syncthreads_or(build_masks(sm, with_eq) != 0);
-    prof.mark(4);
-    if (!any) {
-        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
-        prof.count(10);
-        return;
+    if constexpr (kGreedy) {
+        __syncthreads();
+        prof.mark(3);
+        const bool any = __syncthreads_or(build_masks(sm, with_eq) != 0);
+        prof.mark(4);
+        if (!any) {
+            if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+            prof.count(10);
+            return;
+        }
+        prof.count(11);
     }
-    prof.count(11);
     emit_chunk<kGreedy>(sm, chunk, with_eq, out, id_of, prof);
 }
 
@@ -895,6 +933,10 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
     prof.mark(0);
     const ChunkFlags fl = reduce_flags(sm, v_or, v_and, o_and);   // barrier: occupancy interior published
     prof.mark(1);
+#if defined(VXP_EXP_STOP) && VXP_EXP_STOP == 1
+    if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};   // timing experiment: stream + convert only
+    return;
+#endif
     if (bnd.tags) publish_boundary(sm, bnd, chunk, fl);
     if (!fl.any_solid) {                        // all air: no faces
         if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
@@ -903,6 +945,10 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
     }
     const bool halo_air = __syncthreads_or(load_halo(sm, voxels, nb, n, bnd, rows, prof));   // barrier: halo published
     prof.mark(2);
+#if defined(VXP_EXP_STOP) && VXP_EXP_STOP == 2
+    if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};   // timing experiment: ... + halo
+    return;
+#endif
     if (fl.all_solid && !halo_air) {            // buried: no faces
         if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
         prof.count(9);
