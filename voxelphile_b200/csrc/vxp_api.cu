@@ -32,6 +32,11 @@ struct vxp_ctx {
     vxp_chunk_meta* h_meta = nullptr; size_t h_meta_cap = 0;
     uint64_t* h_verts = nullptr;    uint32_t* h_indices = nullptr; size_t h_quads_cap = 0;
     uint64_t* h_total = nullptr;
+    // host-level pipeline (vxp_mesh_chunks_host): copy streams, per-slice events and running totals
+    static constexpr int kMaxSlices = 8;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_h2d[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
+    uint64_t* h_totals = nullptr;   // pinned, kMaxSlices entries
 };
 
 namespace {
@@ -225,6 +230,14 @@ vxp_status vxp_ctx_create(int device, vxp_ctx** out) {
     if (e == cudaSuccess) e = vxp::configure_device();
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_total), sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_total), sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_totals), vxp_ctx::kMaxSlices * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming);
+    for (int k = 0; k < vxp_ctx::kMaxSlices && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_k[k], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         vxp_status s = cuda_fail(nullptr, e, "ctx_create");
         vxp_ctx_destroy(ctx);
@@ -252,6 +265,14 @@ void vxp_ctx_destroy(vxp_ctx* ctx) {
     cudaFreeHost(ctx->h_verts);
     cudaFreeHost(ctx->h_indices);
     cudaFreeHost(ctx->h_total);
+    cudaFreeHost(ctx->h_totals);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    for (int k = 0; k < vxp_ctx::kMaxSlices; ++k) {
+        if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
+        if (ctx->ev_k[k]) cudaEventDestroy(ctx->ev_k[k]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -386,6 +407,11 @@ vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
     return VXP_OK;
 }
 
+// Host voxels in, host mesh out.  The batch is cut into slices; the upload of slice k+1, the meshing of
+// slice k and the download of the quads of slice k-1 overlap (PCIe is full duplex and the kernel is ~50x
+// faster than either copy), so the call costs about as much as the upload alone.  A slice is meshed as soon
+// as every chunk its neighbour table names has arrived.  If the output arena turns out too small the
+// kernels are re-run (voxels are on the device by then) through the plain path.
 vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int32_t* nbr6, uint32_t n,
                                 uint32_t n_stored, vxp_mode mode, vxp_mesh_host* out) {
     if (!ctx || !out || !valid_mode(mode) || n_stored < n || (n && !voxels)) return VXP_ERR_BAD_ARG;
@@ -396,20 +422,96 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
     vxp_status s;
     if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n_stored, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_nbr6, &ctx->nbr_cap, n, 6)) != VXP_OK) return s;
-    if (n) {
-        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels, voxels, (size_t)n_stored * VXP_CHUNK_VOXELS * sizeof(uint16_t),
-                                      cudaMemcpyHostToDevice, ctx->stream));
-        if (nbr6)
-            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t),
-                                          cudaMemcpyHostToDevice, ctx->stream));
-    }
+    if ((s = grow_device(ctx, &ctx->d_meta, &ctx->meta_cap, n, 1)) != VXP_OK) return s;
+    if ((s = grow_pinned(ctx, &ctx->h_meta, &ctx->h_meta_cap, n, 1)) != VXP_OK) return s;
+    if ((s = grow_quads(ctx, (size_t)n * 512 + 4096)) != VXP_OK) return s;       // first guess; grows on overflow
+    if ((s = grow_host_quads(ctx, ctx->quads_cap)) != VXP_OK) return s;
     const int32_t* d_nbr = nbr6 ? ctx->d_nbr6 : nullptr;
+    const int greedy = mode == VXP_MODE_GREEDY;
+    const size_t chunk_bytes = (size_t)VXP_CHUNK_VOXELS * sizeof(uint16_t);
+    uint64_t total = 0;
+    bool done = false;
+    if (n) {
+        const uint32_t S = n >= 2048 ? 8u : n >= 256 ? 4u : 1u;
+        const uint32_t slice = (n + S - 1) / S;
+        // slice whose upload completes the inputs of slice k
+        uint32_t need[vxp_ctx::kMaxSlices];
+        for (uint32_t k = 0; k < S; ++k) {
+            uint32_t hi_ref = k;
+            if (nbr6) {
+                const uint32_t lo = k * slice, hi = lo + slice < n ? lo + slice : n;
+                for (size_t i = (size_t)lo * 6; i < (size_t)hi * 6; ++i)
+                    if (nbr6[i] >= 0 && (uint32_t)nbr6[i] < n && (uint32_t)nbr6[i] / slice > hi_ref) hi_ref = (uint32_t)nbr6[i] / slice;
+            }
+            need[k] = hi_ref < S ? hi_ref : S - 1;
+        }
+        vxp::BoundaryScratch scratch{nullptr, nullptr, 0};
+        if ((s = next_boundary_scratch(ctx, n, &scratch)) != VXP_OK) return s;
+        const vxp_mesh_dev dev{ctx->d_verts, ctx->d_indices, ctx->d_meta, ctx->d_total, ctx->quads_cap};
+        // uploads: neighbour table and read-only halo chunks first, then the slices in order
+        VXP_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+        VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+        VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+        if (nbr6)
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_in));
+        if (n_stored > n)
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels + (size_t)n * VXP_CHUNK_VOXELS, voxels + (size_t)n * VXP_CHUNK_VOXELS,
+                                          (size_t)(n_stored - n) * chunk_bytes, cudaMemcpyHostToDevice, ctx->s_in));
+        for (uint32_t k = 0; k < S; ++k) {
+            const uint32_t lo = k * slice, hi = lo + slice < n ? lo + slice : n;
+            if (lo < hi)
+                VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels + (size_t)lo * VXP_CHUNK_VOXELS, voxels + (size_t)lo * VXP_CHUNK_VOXELS,
+                                              (size_t)(hi - lo) * chunk_bytes, cudaMemcpyHostToDevice, ctx->s_in));
+            VXP_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[k], ctx->s_in));
+        }
+        // kernels: slice k once slice need[k] is on the device; the running total follows each one to the host
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_total, 0, sizeof(uint64_t), ctx->stream));
+        for (uint32_t k = 0; k < S; ++k) {
+            VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[need[k]], 0));
+            VXP_CUDA(ctx, vxp::launch_mesh_range(ctx->d_voxels, d_nbr, n, k * slice, (k + 1) * slice, greedy, dev, scratch, ctx->stream));
+            ctx->launches += 1;
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_totals + k, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            VXP_CUDA(ctx, cudaEventRecord(ctx->ev_k[k], ctx->stream));
+        }
+        // downloads: the quads of slice k as soon as its kernel is done
+        uint64_t prev = 0;
+        bool overflow = false;
+        for (uint32_t k = 0; k < S; ++k) {
+            VXP_CUDA(ctx, cudaEventSynchronize(ctx->ev_k[k]));
+            const uint64_t t = ctx->h_totals[k];
+            if (t > ctx->quads_cap) { overflow = true; total = t; continue; }
+            if (!overflow && t > prev) {
+                VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_verts + prev * 4, ctx->d_verts + prev * 4, (t - prev) * 4 * sizeof(uint64_t),
+                                              cudaMemcpyDeviceToHost, ctx->s_out));
+                VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices + prev * 6, ctx->d_indices + prev * 6, (t - prev) * 6 * sizeof(uint32_t),
+                                              cudaMemcpyDeviceToHost, ctx->s_out));
+            }
+            prev = t;
+        }
+        if (!overflow) {
+            total = prev;
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_meta, ctx->d_meta, (size_t)n * sizeof(vxp_chunk_meta), cudaMemcpyDeviceToHost, ctx->s_out));
+            VXP_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+            done = true;
+        } else {
+            VXP_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+            VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if ((s = grow_quads(ctx, total)) != VXP_OK) return s;
+        }
+    }
+    if (done || n == 0) {
+        out->verts = ctx->h_verts;
+        out->indices = ctx->h_indices;
+        out->meta = ctx->h_meta;
+        out->total_quads = total;
+        return VXP_OK;
+    }
     return mesh_into_host(
         ctx, n,
         [&](const vxp_mesh_dev& dev) {
             vxp::BoundaryScratch scratch{nullptr, nullptr, 0};
-            if (n && next_boundary_scratch(ctx, n, &scratch) != VXP_OK) return cudaErrorMemoryAllocation;
-            return vxp::launch_mesh(ctx->d_voxels, d_nbr, n, mode == VXP_MODE_GREEDY, dev, scratch, ctx->stream);
+            if (next_boundary_scratch(ctx, n, &scratch) != VXP_OK) return cudaErrorMemoryAllocation;
+            return vxp::launch_mesh(ctx->d_voxels, d_nbr, n, greedy, dev, scratch, ctx->stream);
         },
         out);
 }

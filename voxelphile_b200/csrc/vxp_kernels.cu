@@ -212,16 +212,23 @@ static v4::MeshOut mesh_out(const vxp_mesh_dev& o) {
                        reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads};
 }
 
+cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi,
+                              int greedy, const vxp_mesh_dev& o, const BoundaryScratch& scratch, cudaStream_t stream) {
+    if (hi > n) hi = n;
+    if (lo >= hi) return cudaSuccess;
+    const v4::Bnd bnd{scratch.tags, scratch.planes, scratch.epoch};
+    if (greedy)
+        v4::mesh_kernel<true><<<hi - lo, kThreads, sizeof(v4::Smem<true>), stream>>>(d_voxels, d_nbr6, n, lo, mesh_out(o), bnd);
+    else
+        v4::mesh_kernel<false><<<hi - lo, kThreads, sizeof(v4::Smem<false>), stream>>>(d_voxels, d_nbr6, n, lo, mesh_out(o), bnd);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, int greedy,
                         const vxp_mesh_dev& o, const BoundaryScratch& scratch, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
     if (e != cudaSuccess || n == 0) return e;
-    const v4::Bnd bnd{scratch.tags, scratch.planes, scratch.epoch};
-    if (greedy)
-        v4::mesh_kernel<true><<<n, kThreads, sizeof(v4::Smem<true>), stream>>>(d_voxels, d_nbr6, n, mesh_out(o), bnd);
-    else
-        v4::mesh_kernel<false><<<n, kThreads, sizeof(v4::Smem<false>), stream>>>(d_voxels, d_nbr6, n, mesh_out(o), bnd);
-    return cudaGetLastError();
+    return launch_mesh_range(d_voxels, d_nbr6, n, 0, n, greedy, o, scratch, stream);
 }
 
 size_t boundary_tag_bytes(uint32_t n) { return (size_t)n * sizeof(uint32_t); }

@@ -25,6 +25,9 @@ cudaError_t launch_pattern_fill(const vxp_coord* d_coords, uint32_t n, int patte
                                 cudaStream_t stream);
 cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, int greedy,
                         const vxp_mesh_dev& out, const BoundaryScratch& scratch, cudaStream_t stream);
+// chunks [lo, hi) of a batch of n; does NOT zero *out.total_quads (ranges of one batch accumulate into it)
+cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi,
+                              int greedy, const vxp_mesh_dev& out, const BoundaryScratch& scratch, cudaStream_t stream);
 cudaError_t launch_terrain_mesh(const vxp_coord* d_coords, uint32_t n, uint64_t seed, int greedy,
                                 const vxp_mesh_dev& out, cudaStream_t stream);
 }  // namespace vxp

@@ -899,11 +899,12 @@ __device__ __forceinline__ void issue_slab(Smem<kGreedy>& sm, const uint16_t* gv
 
 template <bool kGreedy>
 __global__ void __launch_bounds__(kThreads, 3)
-mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, MeshOut out, Bnd bnd) {
+mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, uint32_t chunk0, MeshOut out,
+            Bnd bnd) {   // meshes chunks [chunk0, min(chunk0 + gridDim.x, n)) of a batch of n
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<kGreedy>& sm = *reinterpret_cast<Smem<kGreedy>*>(smem_raw);
     const int tid = threadIdx.x;
-    const uint32_t chunk = blockIdx.x;
+    const uint32_t chunk = chunk0 + blockIdx.x;
     if (chunk >= n) return;
     const uint16_t* gvox = voxels + (size_t)chunk * VXP_CHUNK_VOXELS;
     Prof prof;
