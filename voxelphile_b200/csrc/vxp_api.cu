@@ -29,6 +29,9 @@ struct vxp_ctx {
     // boundary-summary scratch of the mesh kernel (vxp_launch.h: BoundaryScratch)
     uint32_t* d_tags = nullptr;     unsigned long long* d_planes = nullptr;  size_t bnd_cap = 0;   // chunks
     uint32_t epoch = 0;
+    // column scratch of the fused terrain+mesh path (vxp_launch.h: ColumnScratch)
+    unsigned char* d_columns = nullptr;  size_t columns_cap = 0;   // chunks
+    vxp::ColumnScratch columns{};
     vxp_chunk_meta* h_meta = nullptr; size_t h_meta_cap = 0;
     uint64_t* h_verts = nullptr;    uint32_t* h_indices = nullptr; size_t h_quads_cap = 0;
     uint64_t* h_total = nullptr;
@@ -139,6 +142,32 @@ vxp_status next_boundary_scratch(vxp_ctx* ctx, uint32_t n, vxp::BoundaryScratch*
         ctx->epoch = 1;
     }
     *out = vxp::BoundaryScratch{ctx->d_tags, ctx->d_planes, ctx->epoch};
+    return VXP_OK;
+}
+
+// Column scratch for a fused launch over n chunks: one allocation carved into the ColumnScratch arrays.
+vxp_status column_scratch(vxp_ctx* ctx, uint32_t n, vxp::ColumnScratch* out) {
+    if (n > ctx->columns_cap) {
+        const size_t want = (size_t)n + n / 4;
+        const size_t slots = vxp::column_table_slots((uint32_t)want);
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_keys = up(slots * 8), b_ids = up(slots * 4), b_slot = up(want * 8), b_coord = up(want * 8),
+                     b_h = up(want * vxp::column_record_bytes()), b_cnt = 256;
+        if (ctx->d_columns) VXP_CUDA(ctx, cudaFree(ctx->d_columns));
+        ctx->d_columns = nullptr;
+        ctx->columns_cap = 0;
+        VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_columns), b_keys + b_ids + b_slot + b_coord + b_h + b_cnt));
+        unsigned char* p = ctx->d_columns;
+        ctx->columns.keys = reinterpret_cast<unsigned long long*>(p); p += b_keys;
+        ctx->columns.id_of_slot = reinterpret_cast<uint32_t*>(p); p += b_ids;
+        ctx->columns.slot_of_chunk = reinterpret_cast<uint32_t*>(p); p += b_slot;
+        ctx->columns.coord_of_id = reinterpret_cast<int2*>(p); p += b_coord;
+        ctx->columns.heights = reinterpret_cast<short*>(p); p += b_h;
+        ctx->columns.count = reinterpret_cast<uint32_t*>(p);
+        ctx->columns.mask = (uint32_t)(slots - 1);
+        ctx->columns_cap = want;
+    }
+    *out = ctx->columns;
     return VXP_OK;
 }
 
@@ -259,6 +288,7 @@ void vxp_ctx_destroy(vxp_ctx* ctx) {
     cudaFree(ctx->d_verts);
     cudaFree(ctx->d_indices);
     cudaFree(ctx->d_total);
+    cudaFree(ctx->d_columns);
     cudaFree(ctx->d_tags);
     cudaFree(ctx->d_planes);
     cudaFreeHost(ctx->h_meta);
@@ -382,7 +412,12 @@ vxp_status vxp_terrain_mesh_fused(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
                                   vxp_mode mode, const vxp_mesh_dev* out) {
     if (!ctx || !valid_mode(mode) || !valid_out(out, n) || (n && !d_coords)) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
-    VXP_CUDA(ctx, vxp::launch_terrain_mesh(d_coords, n, seed, mode == VXP_MODE_GREEDY, *out, ctx->stream));
+    vxp::ColumnScratch cols{};
+    if (n) {
+        const vxp_status s = column_scratch(ctx, n, &cols);
+        if (s != VXP_OK) return s;
+    }
+    VXP_CUDA(ctx, vxp::launch_terrain_mesh(d_coords, n, seed, mode == VXP_MODE_GREEDY, *out, cols, ctx->stream));
     ctx->launches += n ? 1 : 0;
     return VXP_OK;
 }
@@ -528,7 +563,9 @@ vxp_status vxp_terrain_mesh_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
     return mesh_into_host(
         ctx, n,
         [&](const vxp_mesh_dev& dev) {
-            return vxp::launch_terrain_mesh(ctx->d_coords, n, seed, mode == VXP_MODE_GREEDY, dev, ctx->stream);
+            vxp::ColumnScratch cols{};
+            if (n && column_scratch(ctx, n, &cols) != VXP_OK) return cudaErrorMemoryAllocation;
+            return vxp::launch_terrain_mesh(ctx->d_coords, n, seed, mode == VXP_MODE_GREEDY, dev, cols, ctx->stream);
         },
         out);
 }

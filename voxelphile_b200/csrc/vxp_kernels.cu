@@ -81,55 +81,112 @@ __global__ void __launch_bounds__(kThreads) pattern_fill_kernel(const vxp_coord*
 // v4::mesh_kernel lives in vxp_mesh4.cuh (one CTA per chunk, three CTAs per SM).
 
 // ====================================================================== fused terrain + mesh
-// The tile is generated in shared memory from the height field; voxels never reach HBM and the
-// halo comes straight from the heights of the 34x34 column footprint.
-template <bool kGreedy>
-__global__ void __launch_bounds__(kThreads, 3)
-terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t seed, v4::MeshOut out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    v4::Smem<kGreedy>& sm = *reinterpret_cast<v4::Smem<kGreedy>*>(smem_raw);
-    __shared__ short s_h[34 * 34];   // heights of the column footprint: s_h[(z+1)*34 + (x+1)]  (|h-256| <= 720)
-    __shared__ int s_red[2 * kWarps];
-    __shared__ TerrainLattice s_lat;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t chunk = blockIdx.x;
-    if (chunk >= n) return;
-    const vxp_coord c = coords[chunk];
-    const TerrainKeys tk = terrain_keys(seed);
-    v4::Prof prof;
-    prof.start(tid == 0);
-    if (tid == 0) sm.ones = kFull;
-    terrain_lattice_fill(s_lat, tk, 32 * c.x - 1, 32 * c.z - 1);
-    __syncthreads();
+// Terrain is a function of the (x,z) column only, so the chunks of a batch that share a column coordinate
+// (cx,cz) share their 34x34 height footprint.  Three launches:
+//   column_insert_kernel   one thread per chunk: find-or-insert (cx,cz) in an open-addressing hash table
+//                          (atomicCAS on 64-bit keys); the inserting thread draws the column's id
+//   column_heights_kernel  persistent CTAs, one column at a time: lattice gradients, 34x34 heights, min / max
+//   terrain_mesh_kernel    one CTA per chunk: read min / max (most chunks of a world are entirely above or
+//                          below the surface and stop there), else the footprint, build the tile in shared
+//                          memory and run the meshing pipeline of vxp_mesh4.cuh; voxels never reach HBM.
+constexpr int kColStride = 34 * 34 + 4;            // shorts per column record: footprint, hmin, hmax, 2 pad (8-byte multiple)
+constexpr unsigned long long kEmptyKey = ~0ull;
 
-    int hmin = INT_MAX, hmax = INT_MIN;
-    for (int i = tid; i < 34 * 34; i += kThreads) {
-        const int zz = i / 34 - 1, xx = i % 34 - 1;
-        const bool corner = (zz < 0 || zz > 31) && (xx < 0 || xx > 31);
-        int h = 0;
-        if (!corner) {
-            h = terrain_height_lattice(s_lat, 32 * c.x + xx, 32 * c.z + zz);
-            hmin = min(hmin, h);
-            hmax = max(hmax, h);
+__device__ __forceinline__ unsigned long long column_key(int cx, int cz) {
+    return ((unsigned long long)(uint32_t)cx << 32 | (uint32_t)cz) ^ 0x8000000080000000ull;   // never kEmptyKey for sane coords
+}
+__global__ void __launch_bounds__(kThreads) column_insert_kernel(const vxp_coord* __restrict__ coords, uint32_t n,
+                                                                  ColumnScratch cs) {
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const vxp_coord c = coords[i];
+    const unsigned long long key = column_key(c.x, c.z);
+    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & cs.mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(cs.keys + slot, kEmptyKey, key);
+        if (old == kEmptyKey) {                      // we created the column
+            const uint32_t id = atomicAdd(cs.count, 1u);
+            cs.id_of_slot[slot] = id;
+            cs.coord_of_id[id] = make_int2(c.x, c.z);
+            break;
         }
-        s_h[i] = (short)h;
+        if (old == key) break;
+        slot = (slot + 1) & cs.mask;
     }
+    cs.slot_of_chunk[i] = slot;
+}
+__global__ void __launch_bounds__(kThreads) column_heights_kernel(ColumnScratch cs, uint64_t seed) {
+    __shared__ TerrainLattice s_lat;
+    __shared__ int s_red[2 * kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TerrainKeys tk = terrain_keys(seed);
+    const uint32_t ncols = *cs.count;
+    for (uint32_t col = blockIdx.x; col < ncols; col += gridDim.x) {
+        const int2 c = cs.coord_of_id[col];
+        terrain_lattice_fill(s_lat, tk, 32 * c.x - 1, 32 * c.y - 1);
+        __syncthreads();
+        short* dst = cs.heights + (size_t)col * kColStride;
+        int hmin = INT_MAX, hmax = INT_MIN;
+        for (int i = tid; i < 34 * 34; i += kThreads) {
+            const int zz = i / 34 - 1, xx = i % 34 - 1;
+            const bool corner = (zz < 0 || zz > 31) && (xx < 0 || xx > 31);
+            int h = 0;
+            if (!corner) {
+                h = terrain_height_lattice(s_lat, 32 * c.x + xx, 32 * c.y + zz);
+                hmin = min(hmin, h);
+                hmax = max(hmax, h);
+            }
+            dst[i] = (short)h;
+        }
+        hmin = __reduce_min_sync(kFull, hmin);
+        hmax = __reduce_max_sync(kFull, hmax);
+        if (lane == 0) { s_red[warp] = hmin; s_red[kWarps + warp] = hmax; }
+        __syncthreads();
+        if (tid == 0) {
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        hmin = min(hmin, __shfl_xor_sync(kFull, hmin, d));
-        hmax = max(hmax, __shfl_xor_sync(kFull, hmax, d));
+            for (int w = 0; w < kWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kWarps + w]); }
+            dst[34 * 34] = (short)hmin;
+            dst[34 * 34 + 1] = (short)hmax;
+        }
+        __syncthreads();
     }
-    if (lane == 0) { s_red[warp] = hmin; s_red[kWarps + warp] = hmax; }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kWarps + w]); }
+}
 
-    const int Y0 = 32 * c.y;
-    // all air (incl. the layer below it) or all solid incl. every halo layer: no visible face
-    if (Y0 > hmax || Y0 + 32 <= hmin) {
-        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
-        return;
+// One thread per chunk: chunks that are all air (including the layer below them) or all solid including every
+// halo layer have no visible face and are finished here; the others go on the work list of the mesh kernel.
+__global__ void __launch_bounds__(kThreads) column_classify_kernel(const vxp_coord* __restrict__ coords, uint32_t n,
+                                                                    ColumnScratch cs, vxp_chunk_meta* __restrict__ meta) {
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool surface = false;
+    if (i < n) {
+        const short* col = cs.heights + (size_t)cs.id_of_slot[cs.slot_of_chunk[i]] * kColStride;
+        const int hmin = col[34 * 34], hmax = col[34 * 34 + 1], Y0 = 32 * coords[i].y;
+        surface = !(Y0 > hmax || Y0 + 32 <= hmin);
+        if (!surface) meta[i] = vxp_chunk_meta{0u, 0u};
     }
+    const uint32_t m = __ballot_sync(kFull, surface);          // one list reservation per warp
+    if (m == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(cs.count + 1, (uint32_t)__popc(m));
+    base = __shfl_sync(kFull, base, 0);
+    if (surface) cs.slot_of_chunk[n + base + __popc(m & ((1u << lane) - 1u))] = i;   // work list lives behind slot_of_chunk
+}
+
+// One surface chunk: footprint -> tile in shared memory -> the meshing pipeline of vxp_mesh4.cuh.
+template <bool kGreedy>
+__device__ __forceinline__ void terrain_mesh_chunk(v4::Smem<kGreedy>& sm, short* s_h, const vxp_coord* __restrict__ coords,
+                                                   const ColumnScratch& cs, uint32_t chunk, const v4::MeshOut& out) {
+    const int tid = threadIdx.x;
+    const vxp_coord c = coords[chunk];
+    v4::Prof prof;
+    prof.start(false);
+    const short* col = cs.heights + (size_t)cs.id_of_slot[cs.slot_of_chunk[chunk]] * kColStride;
+    const int Y0 = 32 * c.y;
+    if (tid == 0) sm.ones = kFull;
+    for (int i = tid; i < 34 * 34 / 2; i += kThreads)     // 2312 bytes, 4 at a time
+        reinterpret_cast<uint32_t*>(s_h)[i] = __ldg(reinterpret_cast<const uint32_t*>(col) + i);
+    __syncthreads();
     // tile
     uint4* tile4 = reinterpret_cast<uint4*>(sm.tile.vox);
 #pragma unroll 2
@@ -178,6 +235,25 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t s
     }, prof);
 }
 
+template <bool kGreedy>
+__global__ void __launch_bounds__(kThreads, 3)
+terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, ColumnScratch cs, v4::MeshOut out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    v4::Smem<kGreedy>& sm = *reinterpret_cast<v4::Smem<kGreedy>*>(smem_raw);
+    __shared__ short s_h[34 * 34];   // heights of the column footprint: s_h[(z+1)*34 + (x+1)]  (|h-256| <= 720)
+    __shared__ uint32_t s_item[2];
+    const uint32_t nwork = cs.count[1];
+    if (threadIdx.x == 0) s_item[0] = atomicAdd(cs.count + 2, 1u);
+    __syncthreads();
+    for (uint32_t it = 0;; ++it) {                    // work items are drawn from a ticket counter: chunk costs vary widely
+        const uint32_t item = s_item[it & 1];
+        if (item >= nwork) break;
+        if (threadIdx.x == 0) s_item[(it + 1) & 1] = atomicAdd(cs.count + 2, 1u);   // its latency hides behind this chunk
+        terrain_mesh_chunk(sm, s_h, coords, cs, cs.slot_of_chunk[n + item], out);
+        __syncthreads();                              // shared memory is free again, the next ticket is visible
+    }
+}
+
 // ====================================================================== launchers
 
 template <class K>
@@ -217,10 +293,11 @@ cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, u
     if (hi > n) hi = n;
     if (lo >= hi) return cudaSuccess;
     const v4::Bnd bnd{scratch.tags, scratch.planes, scratch.epoch};
+    const uint32_t grid = hi - lo;
     if (greedy)
-        v4::mesh_kernel<true><<<hi - lo, kThreads, sizeof(v4::Smem<true>), stream>>>(d_voxels, d_nbr6, n, lo, mesh_out(o), bnd);
+        v4::mesh_kernel<true><<<grid, kThreads, sizeof(v4::Smem<true>), stream>>>(d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd);
     else
-        v4::mesh_kernel<false><<<hi - lo, kThreads, sizeof(v4::Smem<false>), stream>>>(d_voxels, d_nbr6, n, lo, mesh_out(o), bnd);
+        v4::mesh_kernel<false><<<grid, kThreads, sizeof(v4::Smem<false>), stream>>>(d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd);
     return cudaGetLastError();
 }
 
@@ -265,14 +342,33 @@ extern "C" int vxp_debug_read_prof(unsigned long long* out, int max_ctas) {
 }
 #endif
 
+size_t column_table_slots(uint32_t n) {
+    size_t t = 64;
+    while (t < 2 * (size_t)n) t <<= 1;
+    return t;
+}
+size_t column_record_bytes() { return kColStride * sizeof(short); }
+
 cudaError_t launch_terrain_mesh(const vxp_coord* d_coords, uint32_t n, uint64_t seed, int greedy,
-                                const vxp_mesh_dev& o, cudaStream_t stream) {
+                                const vxp_mesh_dev& o, const ColumnScratch& cs, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
     if (e != cudaSuccess || n == 0) return e;
+    e = cudaMemsetAsync(cs.keys, 0xFF, ((size_t)cs.mask + 1) * sizeof(unsigned long long), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cs.count, 0, 3 * sizeof(uint32_t), stream);   // columns, work items, ticket
+    if (e != cudaSuccess) return e;
+    column_insert_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_coords, n, cs);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t hgrid = n < (uint32_t)(4 * sms) ? n : (uint32_t)(4 * sms);
+    column_heights_kernel<<<hgrid, kThreads, 0, stream>>>(cs, seed);
+    column_classify_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_coords, n, cs, o.meta);
+    // the work list's length is only known on the device: a resident grid strides over it
+    const uint32_t mgrid = n < (uint32_t)(3 * sms) ? n : (uint32_t)(3 * sms);
     if (greedy)
-        terrain_mesh_kernel<true><<<n, kThreads, sizeof(v4::Smem<true>), stream>>>(d_coords, n, seed, mesh_out(o));
+        terrain_mesh_kernel<true><<<mgrid, kThreads, sizeof(v4::Smem<true>), stream>>>(d_coords, n, cs, mesh_out(o));
     else
-        terrain_mesh_kernel<false><<<n, kThreads, sizeof(v4::Smem<false>), stream>>>(d_coords, n, seed, mesh_out(o));
+        terrain_mesh_kernel<false><<<mgrid, kThreads, sizeof(v4::Smem<false>), stream>>>(d_coords, n, cs, mesh_out(o));
     return cudaGetLastError();
 }
 

@@ -17,6 +17,23 @@ struct BoundaryScratch {
 size_t boundary_tag_bytes(uint32_t n);
 size_t boundary_plane_bytes(uint32_t n);
 
+// Context-owned scratch of the fused terrain+mesh path: the chunks of a batch that share a column (cx,cz)
+// share one height footprint.  Sized for a batch of n chunks: keys / id_of_slot have column_table_slots(n)
+// entries (a power of two, mask = slots - 1), slot_of_chunk has 2n (the second half is the work list of
+// chunks that cross the surface), coord_of_id n, heights n records of column_record_bytes(), count 3 words
+// (columns, work items, ticket).  Nothing needs initialising by the owner.
+struct ColumnScratch {
+    unsigned long long* keys;
+    uint32_t* id_of_slot;
+    uint32_t* slot_of_chunk;
+    int2* coord_of_id;
+    short* heights;
+    uint32_t* count;
+    uint32_t mask;
+};
+size_t column_table_slots(uint32_t n);
+size_t column_record_bytes();
+
 // per-device one-time setup (opt-in shared memory size); call with the device current
 cudaError_t configure_device();
 cudaError_t launch_terrain_fill(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
@@ -29,5 +46,5 @@ cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_
 cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi,
                               int greedy, const vxp_mesh_dev& out, const BoundaryScratch& scratch, cudaStream_t stream);
 cudaError_t launch_terrain_mesh(const vxp_coord* d_coords, uint32_t n, uint64_t seed, int greedy,
-                                const vxp_mesh_dev& out, cudaStream_t stream);
+                                const vxp_mesh_dev& out, const ColumnScratch& columns, cudaStream_t stream);
 }  // namespace vxp

@@ -236,7 +236,11 @@ __device__ __forceinline__ void publish_boundary(const SM& sm, const Bnd& bnd, u
 // Fill the halo of sm.occ / sm.xh: warp f < 6 produces the 32 words of face f.  Returns (per
 // thread) whether any halo bit this thread produced is air.  Contains no barrier.
 // nb = neighbour index of face f = warp index (loaded by the caller before the tile wait).
-constexpr int kPlanePolls = 3;   // bounded re-reads of a boundary plane that is not there yet (never a wait-for)
+#ifndef VXP_PLANE_POLLS
+#define VXP_PLANE_POLLS 8
+#endif
+constexpr int kPlanePolls = VXP_PLANE_POLLS;   // bounded re-reads of a boundary plane that is not there yet (never a wait-for);
+                                               // measured on config 2: 1 -> 109.4 us, 3 -> 104.9, 6 -> 104.1, 12 -> 103.5
 template <class SM>
 __device__ __forceinline__ bool load_halo(SM& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n,
                                           const Bnd& bnd, const HaloRows& rows, Prof& prof) {
@@ -897,24 +901,17 @@ __device__ __forceinline__ void issue_slab(Smem<kGreedy>& sm, const uint16_t* gv
                 reinterpret_cast<const unsigned char*>(gvox) + s * kSlabBytes, kSlabBytes, &sm.mbar[s]);
 }
 
+// One chunk, start to finish.  The four tile barriers have been initialised by the caller and complete once
+// per chunk: `parity` is the phase to wait for (0 for the first chunk of a CTA, then alternating).
+// Every return is block-uniform.
 template <bool kGreedy>
-__global__ void __launch_bounds__(kThreads, 3)
-mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, uint32_t chunk0, MeshOut out,
-            Bnd bnd) {   // meshes chunks [chunk0, min(chunk0 + gridDim.x, n)) of a batch of n
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem<kGreedy>& sm = *reinterpret_cast<Smem<kGreedy>*>(smem_raw);
+__device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6,
+                                           uint32_t n, uint32_t chunk, uint32_t parity, const MeshOut& out, const Bnd& bnd) {
     const int tid = threadIdx.x;
-    const uint32_t chunk = chunk0 + blockIdx.x;
-    if (chunk >= n) return;
     const uint16_t* gvox = voxels + (size_t)chunk * VXP_CHUNK_VOXELS;
     Prof prof;
     prof.start(tid == 0);
-
     if (tid == 0) {
-        sm.ones = kFull;
-#pragma unroll
-        for (int s = 0; s < kSlabs; ++s) mbar_init(&sm.mbar[s], 1);
-        fence_mbar_init();
 #pragma unroll
         for (int s = 0; s < kSlabsInFlight; ++s) issue_slab(sm, gvox, s);
     }
@@ -922,12 +919,11 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
     const int nb = (nbr6 && tid < 192) ? __ldg(nbr6 + 6 * (size_t)chunk + (tid >> 5)) : -1;
     HaloRows rows;
     issue_yz_halo(rows, voxels, nb);
-    __syncthreads();                            // barrier init visible to all waiters
 
     uint32_t v_or = 0, v_and = kFull, o_and = kFull;
 #pragma unroll 1
     for (int s = 0; s < kSlabs; ++s) {
-        mbar_wait(&sm.mbar[s], 0);
+        mbar_wait(&sm.mbar[s], parity);
         if (tid == 0 && s + kSlabsInFlight < kSlabs) issue_slab(sm, gvox, s + kSlabsInFlight);
         convert_slab(sm, s, v_or, v_and, o_and);
     }
@@ -956,6 +952,27 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
         return;
     }
     mesh_tail<kGreedy>(sm, chunk, fl, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
+}
+
+// Meshes chunks [chunk0, hi) of a batch of n, one chunk per CTA (grid = hi - chunk0): the hardware block
+// scheduler is the load balancer.  (Persistent CTAs drawing tickets were measured 7-12 % slower: a CTA
+// that draws its next chunk early delays that chunk's boundary planes for the neighbours that poll them.)
+template <bool kGreedy>
+__global__ void __launch_bounds__(kThreads, 3)
+mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, uint32_t chunk0, uint32_t hi,
+            MeshOut out, Bnd bnd) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem<kGreedy>& sm = *reinterpret_cast<Smem<kGreedy>*>(smem_raw);
+    const uint32_t chunk = chunk0 + blockIdx.x;
+    if (chunk >= hi) return;
+    if (threadIdx.x == 0) {
+        sm.ones = kFull;
+#pragma unroll
+        for (int s = 0; s < kSlabs; ++s) mbar_init(&sm.mbar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();                            // barrier init visible to all
+    mesh_chunk(sm, voxels, nbr6, n, chunk, 0u, out, bnd);
 }
 
 } // namespace v4
