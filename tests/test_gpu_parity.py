@@ -288,3 +288,80 @@ def test_sharded_union_equals_single(mesher):
                 assert np.array_equal(a, b), (world, rank, int(g))
                 seen += 1
         assert seen == len(coords)
+
+
+def _chunk_hashes(host):
+    """Order-independent hash (SPEC §4) of every chunk of a HostMesh, vectorised."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    keys = S.keys_from_verts(host.verts.reshape(-1, 4)) if host.total_quads else np.zeros(0, np.uint64)
+    with np.errstate(over="ignore"):
+        z = keys + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    out = np.zeros(host.meta.shape[0], dtype=np.uint64)
+    owner = np.zeros(host.total_quads, dtype=np.int64)
+    first, cnt = host.meta[:, 0].astype(np.int64), host.meta[:, 1].astype(np.int64)
+    for i in np.nonzero(cnt)[0]:
+        owner[first[i]:first[i] + cnt[i]] = i
+    with np.errstate(over="ignore"):
+        np.add.at(out, owner, z)
+    return out & M
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_full_size_batch_hash_parity(mesher, mode, mname):
+    """BASELINE configs 2 / 3 at full size (4096 terrain chunks, coords [0,16)^3, seed 42): per-chunk quad
+    counts and order-independent key hashes equal the oracle's for every chunk, through the device-level
+    call and through the sliced host-level call."""
+    import torch
+    from voxelphile_b200 import grid_coords, neighbour_table
+    coords = grid_coords((0, 0, 0), (16, 16, 16))
+    nbr = neighbour_table(coords)
+    dvox = mesher.terrain_fill(dev(coords), 42)
+    torch.cuda.synchronize()
+    vox = dvox.cpu().numpy().view(np.uint16)
+    want_hash, want_cnt = O.mesh_batch_hash(vox, nbr, mode)
+    out = mesher.mesh(dvox, dev(nbr), mode, capacity=int(want_cnt.sum()))
+    torch.cuda.synchronize()
+    for host in (out.to_host(), mesher.mesh_host(vox, nbr, mode)):
+        assert host.total_quads == int(want_cnt.sum())
+        assert np.array_equal(host.meta[:, 1], want_cnt)
+        assert np.array_equal(_chunk_hashes(host), want_hash)
+        order = np.argsort(host.meta[:, 0][want_cnt > 0])
+        f, c = host.meta[:, 0][want_cnt > 0][order].astype(np.int64), want_cnt[want_cnt > 0][order].astype(np.int64)
+        assert f[0] == 0 and np.array_equal(f[1:], np.cumsum(c)[:-1]), "ranges must tile [0, Q)"
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_permuted_chunk_order(mesher, mode, mname):
+    """The neighbour table is arbitrary: a terrain block stored in shuffled order (so that x-neighbours are
+    nowhere near each other in the batch) meshes to the same per-chunk result."""
+    import torch
+    from voxelphile_b200 import grid_coords, neighbour_table
+    rng = np.random.default_rng(5)
+    coords = grid_coords((0, 6, 0), (6, 10, 5))
+    coords = coords[rng.permutation(coords.shape[0])]
+    nbr = neighbour_table(coords)
+    dvox = mesher.terrain_fill(dev(coords), 42)
+    torch.cuda.synchronize()
+    vox = dvox.cpu().numpy().view(np.uint16)
+    want_hash, want_cnt = O.mesh_batch_hash(vox, nbr, mode)
+    host = gpu_mesh(mesher, vox, nbr, mode, capacity=int(want_cnt.sum()))
+    assert np.array_equal(host.meta[:, 1], want_cnt)
+    assert np.array_equal(_chunk_hashes(host), want_hash)
+
+
+def test_host_pipeline_with_halo_chunks(mesher):
+    """vxp_mesh_chunks_host in slices (n >= 256) with read-only halo chunks behind the meshed ones and a
+    neighbour table that reaches across slices."""
+    from voxelphile_b200 import grid_coords, neighbour_table
+    from voxelphile_b200.shard import shard_with_halo
+    coords = grid_coords((0, 6, 0), (12, 10, 12))             # 576 chunks
+    vox = O.terrain_fill_batch(42, coords)
+    sh = shard_with_halo(coords, 0, 2)                        # first half owned, seam layer appended
+    want_hash, want_cnt = O.mesh_batch_hash(vox, neighbour_table(coords), 1)
+    host = mesher.mesh_host(vox[sh.batch_index], sh.nbr6, 1, n_mesh=sh.n_owned)
+    assert sh.n_owned >= 256 and len(sh.batch_index) > sh.n_owned
+    assert np.array_equal(host.meta[:, 1], want_cnt[:sh.n_owned])
+    assert np.array_equal(_chunk_hashes(host), want_hash[:sh.n_owned])
