@@ -241,33 +241,60 @@ __device__ __forceinline__ void publish_boundary(const SM& sm, const Bnd& bnd, u
 #endif
 constexpr int kPlanePolls = VXP_PLANE_POLLS;   // bounded re-reads of a boundary plane that is not there yet (never a wait-for);
                                                // measured on config 2: 1 -> 109.4 us, 3 -> 104.9, 6 -> 104.1, 12 -> 103.5
+// The halo is produced in two steps so that callers with something else to do can put it between them:
+// halo_begin   warps 2..5 write their +-Y / +-Z halo rows; warps 0,1 issue the first read of their x
+//              neighbour's tag and boundary plane (two loads in flight together, not waited for)
+// halo_finish  warps 0,1 use what came back, re-read a bounded number of times if the words were not there
+//              yet, and finally gather from the neighbour's voxels; they write sm.xh
+// Both return (per thread) whether any halo bit this thread produced is air.  Neither contains a barrier.
+struct XPoll {
+    unsigned long long pw;
+    uint32_t tag;
+    bool armed;
+};
 template <class SM>
-__device__ __forceinline__ bool load_halo(SM& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n,
-                                          const Bnd& bnd, const HaloRows& rows, Prof& prof) {
+__device__ __forceinline__ bool halo_begin(SM& sm, int nb, uint32_t n, const Bnd& bnd, const HaloRows& rows, XPoll& xp) {
     const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
+    xp.armed = false;
+    xp.tag = 0;
+    xp.pw = 0;
     if (f >= 6) return false;
-    uint32_t word = 0;
     if (f >= 2) {
+        uint32_t word = 0;
         if (nb >= 0) word = nz8(rows.q[0]) | nz8(rows.q[1]) << 8 | nz8(rows.q[2]) << 16 | nz8(rows.q[3]) << 24;
         sm.occ[f == 2 ? (lane + 1) * 34 : f == 3 ? (lane + 1) * 34 + 33 : f == 4 ? lane + 1 : 33 * 34 + lane + 1] = word;
         return word != kFull;
     }
+    if (nb >= 0 && bnd.tags && (uint32_t)nb < n) {
+        xp.tag = ld_relaxed_u32(bnd.tags + nb);
+        xp.pw = ld_relaxed_u64(bnd.planes + (size_t)nb * 64 + (f ^ 1) * 32 + lane);
+        xp.armed = true;
+    }
+    return false;
+}
+template <class SM>
+__device__ __forceinline__ bool halo_finish(SM& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n, const Bnd& bnd,
+                                            XPoll xp, Prof& prof) {
+    const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
+    if (f >= 2) return false;
+    uint32_t word = 0;
     if (nb >= 0) {
         bool have = false;
-        if (bnd.tags && (uint32_t)nb < n) {
+        if (xp.armed) {
             const uint32_t* tagp = bnd.tags + nb;
             const unsigned long long* planep = bnd.planes + (size_t)nb * 64 + (f ^ 1) * 32 + lane;
-            for (int t = 0; t < kPlanePolls && !have; ++t) {
-                const uint32_t tag = ld_relaxed_u32(tagp);             // both loads in flight together
-                const unsigned long long pw = ld_relaxed_u64(planep);
-                if ((tag >> 2) == bnd.epoch) {                          // all air / all solid neighbour
-                    word = (tag & 3u) == kTagSolid ? kFull : 0u;
+            for (int t = 0;; ++t) {
+                if ((xp.tag >> 2) == bnd.epoch) {                       // all air / all solid neighbour
+                    word = (xp.tag & 3u) == kTagSolid ? kFull : 0u;
                     have = true;
-                } else if (__all_sync(kFull, (uint32_t)(pw >> 32) == bnd.epoch)) {
-                    word = (uint32_t)pw;
+                } else if (__all_sync(kFull, (uint32_t)(xp.pw >> 32) == bnd.epoch)) {
+                    word = (uint32_t)xp.pw;
                     have = true;
                 }
                 if (lane == 0) prof.count(15, (unsigned long long)(t + 1));
+                if (have || t + 1 >= kPlanePolls) break;
+                xp.tag = ld_relaxed_u32(tagp);                          // both loads in flight together
+                xp.pw = ld_relaxed_u64(planep);
             }
             if (lane == 0) prof.count(have ? 12 : 13);
         }
@@ -283,6 +310,14 @@ __device__ __forceinline__ bool load_halo(SM& sm, const uint16_t* __restrict__ v
     }
     sm.xh[f][lane] = word;
     return word != kFull;
+}
+template <class SM>
+__device__ __forceinline__ bool load_halo(SM& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n,
+                                          const Bnd& bnd, const HaloRows& rows, Prof& prof) {
+    XPoll xp;
+    const bool a = halo_begin(sm, nb, n, bnd, rows, xp);
+    const bool b = halo_finish(sm, voxels, nb, n, bnd, xp, prof);
+    return a || b;
 }
 
 // ------------------------------------------------------------------ active rows
@@ -691,32 +726,39 @@ __device__ __forceinline__ uint32_t face_word(const SM& sm, int f, int y, int z)
     }
 }
 
-// ------------------------------------------------------------------ masks -> quads -> buffers
-template <bool kGreedy, class IdFn>
-__device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bool with_eq, const MeshOut& out, IdFn id_of,
-                                           Prof& prof) {
+// ------------------------------------------------------------------ culled: occupancy -> quads -> buffers
+// Every visible face is a quad.  No mask arrays, no transposes: thread (warp w, lane z) owns the 24 face
+// words {(f, y, z) : (y + f) % 8 == w} (bit x = face f of voxel (x,y,z) visible) and derives them from the
+// occupancy.  culled_count: quads | non-empty words << 17 of the thread's words of faces [f_lo, f_hi) (the
+// words of faces 2..5 do not depend on the x halo, so mesh_chunk counts them while that halo is in flight).
+// culled_emit: one packed block scan gives every thread its first ordinal and its slot in the word list;
+// the non-empty words are listed with the ordinal of their first quad; the threads share the list evenly.
+template <bool kGreedy>
+__device__ __forceinline__ uint32_t culled_count(const Smem<kGreedy>& sm, int f_lo, int f_hi) {
+    const int z = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        if (f < f_lo || f >= f_hi) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t word = face_word(sm, f, ((w - f) & 7) + 8 * j, z);
+            packed += (uint32_t)__popc(word) + (word ? 1u << 17 : 0u);
+        }
+    }
+    return packed;
+}
+template <class IdFn>
+__device__ __forceinline__ void culled_emit(Smem<false>& sm, uint32_t chunk, uint32_t packed, const MeshOut& out, IdFn id_of,
+                                            Prof& prof) {
     const int tid = threadIdx.x;
-    constexpr uint32_t kCap = Post<kGreedy>::kCap;
+    constexpr uint32_t kCap = Post<false>::kCap;
     uint32_t* const staging = sm.tile.post.staging;
     auto nothing = [] {};
     auto staged = [staging](uint32_t i) { return staging[i]; };
-    if constexpr (!kGreedy) {
-        // ---- culled: every visible face is a quad.  No mask arrays, no transposes: thread (warp w, lane z) owns
-        // the 24 face words {(f, y, z) : (y + f) % 8 == w} (bit x = face f of voxel (x,y,z) visible) and derives
-        // them from the occupancy.  Pass 1 counts quads and non-empty words (one packed block scan gives every
-        // thread its first ordinal and its slot in the word list); pass 2 writes the non-empty words with the
-        // ordinal of their first quad; pass 3 shares the list evenly between the threads.
+    {
         Post<false>& P = sm.tile.post;
         const int z = tid & 31, w = tid >> 5;
-        uint32_t packed = 0;                                   // quads | non-empty words << 17
-#pragma unroll
-        for (int f = 0; f < 6; ++f) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t word = face_word(sm, f, ((w - f) & 7) + 8 * j, z);
-                packed += (uint32_t)__popc(word) + (word ? 1u << 17 : 0u);
-            }
-        }
         uint32_t tot;
         const uint32_t pre = block_excl_scan(packed, sm.scratch, &tot);
         const uint32_t Q = tot & 0x1FFFFu, nwords = tot >> 17;
@@ -769,6 +811,22 @@ __device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bo
             __syncthreads();
             prof.mark(7);
         }
+        return;
+    }
+}
+
+// ------------------------------------------------------------------ masks -> quads -> buffers
+template <bool kGreedy, class IdFn>
+__device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bool with_eq, const MeshOut& out, IdFn id_of,
+                                           Prof& prof) {
+    const int tid = threadIdx.x;
+    constexpr uint32_t kCap = Post<kGreedy>::kCap;
+    uint32_t* const staging = sm.tile.post.staging;
+    auto nothing = [] {};
+    auto staged = [staging](uint32_t i) { return staging[i]; };
+    if constexpr (!kGreedy) {
+        (void)with_eq;
+        culled_emit(sm, chunk, culled_count(sm, 0, 6), out, id_of, prof);
         return;
     } else {
         // ---- greedy: sweep_log, stage_births, run_height (see above).  The log sits at the end of the
@@ -939,6 +997,22 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
         if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
         prof.count(8);
         return;
+    }
+    if constexpr (!kGreedy) {
+        if (!fl.all_solid) {
+            // Culled, not a buried candidate: count the faces that do not depend on the x halo (+-Y, +-Z: two
+            // thirds of the face words) while the x neighbours' boundary planes are on their way.
+            XPoll xp;
+            halo_begin(sm, nb, n, bnd, rows, xp);
+            __syncthreads();                    // +-Y / +-Z halo rows published
+            uint32_t packed = culled_count(sm, 2, 6);
+            halo_finish(sm, voxels, nb, n, bnd, xp, prof);
+            __syncthreads();                    // x halo published
+            prof.mark(2);
+            packed += culled_count(sm, 0, 2);
+            culled_emit(sm, chunk, packed, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
+            return;
+        }
     }
     const bool halo_air = __syncthreads_or(load_halo(sm, voxels, nb, n, bnd, rows, prof));   // barrier: halo published
     prof.mark(2);
