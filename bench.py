@@ -404,6 +404,36 @@ def main():
         also["greedy" if other == GREEDY else "culled"] = {
             "chunks_per_s": n_step / (ms * 1e-3), "ms_per_step": ms, "hbm_gbs": ob / (ms * 1e-3) / 1e9,
             "frac": ob / (ms * 1e-3) / 1e9 / peak, "quads_per_batch": float(np.mean([c.sum() for c in ocounts]))}
+        # the same workload with two batches in flight (two contexts, two streams): the tail of one launch and the
+        # ramp of the next overlap, which a single in-order stream cannot do
+        m2 = Mesher(local)
+        s2 = torch.cuda.Stream(device=dev)
+        m2.use_stream(s2)
+        out2 = m.alloc_mesh(n_step, max(totals) + 1)
+        pair = [(m, out, stream), (m2, out2, s2)]
+
+        def two(s):
+            mm, oo, _ = pair[s % 2]
+            mm.mesh(batches[s % len(batches)], dnbr, mode, out=oo)
+
+        for s in range(6):
+            two(s)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        s2.wait_event(a)
+        for s in range(120):
+            two(s)
+        j = torch.cuda.Event()
+        j.record(s2)
+        stream.wait_event(j)
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms2 = a.elapsed_time(b) / 120
+        also["two_batches_in_flight"] = {"chunks_per_s": n_step / (ms2 * 1e-3), "ms_per_step": ms2,
+                                         "hbm_gbs": mean_bytes / (ms2 * 1e-3) / 1e9, "frac": mean_bytes / (ms2 * 1e-3) / 1e9 / peak,
+                                         "note": "two contexts on two streams alternate over the same rotating batches"}
+        m2.close()
         if not args.workload.startswith("checker"):
             scratch = torch.empty_like(batches[0])
             ms = timed(lambda s: m.terrain_fill(dcoords, 100 + s, out=scratch))
