@@ -36,6 +36,14 @@ for mode, mn in ((CULLED, "culled"), (GREEDY, "greedy")):
             col = act[sel, i]
             if col.sum() > 0: print(f"        {nm:14s} mean {col.mean():8.0f}  max {col.max():8.0f}")
     for i, nm in counts.items(): print(f"   {nm:20s} {int(act[:, i].sum())}")
+    tb = np.zeros((NC, 2), dtype=np.uint64)
+    lib.vxp_debug_read_prof_time.argtypes = [C.c_void_p, C.c_int]; lib.vxp_debug_read_prof_time(tb.ctypes.data, NC)
+    t0 = tb[:4096, 0].astype(np.int64); t1 = tb[:4096, 1].astype(np.int64); base = t0.min()
+    st, en = (t0 - base) / 1e3, (t1 - base) / 1e3
+    edges = np.arange(0, en.max() + 5, 5.0)
+    conc = [int(((st < e + 5) & (en > e)).sum()) for e in edges]
+    print("   CTAs alive per 5 us bin:", conc)
+    print(f"   first CTA end {en.min():.1f} us, last CTA start {st.max():.1f} us, last end {en.max():.1f} us; CTA life mean {np.mean(en-st):.2f} us; sum of lives / 444 = {np.sum(en-st)/444:.1f} us")
     if mode == GREEDY:
         wb = np.zeros((NC, 8), dtype=np.uint32)
         lib.vxp_debug_read_prof_warp.argtypes = [C.c_void_p, C.c_int]; lib.vxp_debug_read_prof_warp(wb.ctypes.data, NC)

@@ -326,6 +326,10 @@ extern "C" int vxp_debug_occupancy(int greedy, int fused) {
 extern "C" int vxp_debug_smem_bytes(int greedy) { return greedy ? (int)sizeof(v4::Smem<true>) : (int)sizeof(v4::Smem<false>); }
 
 #ifdef VXP_PROFILE
+extern "C" int vxp_debug_read_prof_time(unsigned long long* out, int max_ctas) {
+    const int ctas = max_ctas < v4::kProfCtas ? max_ctas : v4::kProfCtas;
+    return cudaMemcpyFromSymbol(out, v4::g_prof_time, sizeof(unsigned long long) * 2 * (size_t)ctas) == cudaSuccess ? 2 : -1;
+}
 extern "C" int vxp_debug_read_prof_warp(unsigned int* out, int max_ctas) {
     const int ctas = max_ctas < v4::kProfCtas ? max_ctas : v4::kProfCtas;
     return cudaMemcpyFromSymbol(out, v4::g_prof_warp, sizeof(unsigned int) * 8 * (size_t)ctas) == cudaSuccess ? 8 : -1;

@@ -40,6 +40,12 @@ constexpr int kProfSlots = 16;
 constexpr int kProfCtas = 8192;
 __device__ unsigned long long g_prof[kProfCtas][kProfSlots];
 __device__ unsigned int g_prof_warp[kProfCtas][8];   // per-warp cycles of the greedy sweep
+__device__ unsigned long long g_prof_time[kProfCtas][2];   // %globaltimer (ns) at CTA start / end
+__device__ __forceinline__ unsigned long long prof_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 struct Prof {
     long long t;
     bool on;
@@ -1046,7 +1052,13 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
         fence_mbar_init();
     }
     __syncthreads();                            // barrier init visible to all
+#ifdef VXP_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][0] = prof_now();
+#endif
     mesh_chunk(sm, voxels, nbr6, n, chunk, 0u, out, bnd);
+#ifdef VXP_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][1] = prof_now();
+#endif
 }
 
 } // namespace v4
