@@ -733,24 +733,43 @@ __device__ __forceinline__ uint32_t face_word(const SM& sm, int f, int y, int z)
 }
 
 // ------------------------------------------------------------------ culled: occupancy -> quads -> buffers
-// Every visible face is a quad.  No mask arrays, no transposes: thread (warp w, lane z) owns the 24 face
-// words {(f, y, z) : (y + f) % 8 == w} (bit x = face f of voxel (x,y,z) visible) and derives them from the
-// occupancy.  culled_count: quads | non-empty words << 17 of the thread's words of faces [f_lo, f_hi) (the
-// words of faces 2..5 do not depend on the x halo, so mesh_chunk counts them while that halo is in flight).
-// culled_emit: one packed block scan gives every thread its first ordinal and its slot in the word list;
-// the non-empty words are listed with the ordinal of their first quad; the threads share the list evenly.
+// Every visible face is a quad.  No mask arrays, no transposes: thread (warp w, lane y) owns the rows
+// (y, z = 4w + k) and derives their face words (bit x = face f of voxel (x,y,z) visible) from the occupancy:
+// the six words of a row share its five occupancy loads, and a row of air - half of a surface chunk - costs
+// one load and a test.  culled_count: quads | non-empty words << 17 of the thread's words of the x faces
+// (kX) or of the y and z faces, which do not depend on the x halo, so mesh_chunk counts them while that halo
+// is in flight.  culled_emit: one packed block scan gives every thread its first ordinal and its slot in
+// the word list; the non-empty words are listed with the ordinal of their first quad; the threads share the
+// list evenly when they stage the quad records.
 template <bool kGreedy>
-__device__ __forceinline__ uint32_t culled_count(const Smem<kGreedy>& sm, int f_lo, int f_hi) {
-    const int z = threadIdx.x & 31, w = threadIdx.x >> 5;
+__device__ __forceinline__ bool row_words_yz(const Smem<kGreedy>& sm, int y, int z, uint32_t (&wd)[6]) {
+    const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
+    const uint32_t c = o[0];
+    if (c == 0) return false;
+    wd[2] = c & ~o[-1];
+    wd[3] = c & ~o[+1];
+    wd[4] = c & ~o[-34];
+    wd[5] = c & ~o[+34];
+    return true;
+}
+template <bool kGreedy>
+__device__ __forceinline__ bool row_words_x(const Smem<kGreedy>& sm, int y, int z, uint32_t (&wd)[6]) {
+    const uint32_t c = sm.occ[(z + 1) * 34 + (y + 1)];
+    if (c == 0) return false;
+    wd[0] = c & ~((c << 1) | ((sm.xh[0][z] >> y) & 1u));
+    wd[1] = c & ~((c >> 1) | ((sm.xh[1][z] >> y) & 1u) << 31);
+    return true;
+}
+template <bool kX, bool kGreedy>
+__device__ __forceinline__ uint32_t culled_count(const Smem<kGreedy>& sm) {
+    const int y = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t packed = 0;
 #pragma unroll
-    for (int f = 0; f < 6; ++f) {
-        if (f < f_lo || f >= f_hi) continue;
+    for (int k = 0; k < 4; ++k) {
+        uint32_t wd[6];
+        if (!(kX ? row_words_x(sm, y, 4 * w + k, wd) : row_words_yz(sm, y, 4 * w + k, wd))) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t word = face_word(sm, f, ((w - f) & 7) + 8 * j, z);
-            packed += (uint32_t)__popc(word) + (word ? 1u << 17 : 0u);
-        }
+        for (int f = kX ? 0 : 2; f < (kX ? 2 : 6); ++f) packed += (uint32_t)__popc(wd[f]) + (wd[f] ? 1u << 17 : 0u);
     }
     return packed;
 }
@@ -764,7 +783,7 @@ __device__ __forceinline__ void culled_emit(Smem<false>& sm, uint32_t chunk, uin
     auto staged = [staging](uint32_t i) { return staging[i]; };
     {
         Post<false>& P = sm.tile.post;
-        const int z = tid & 31, w = tid >> 5;
+        const int y = tid & 31, w = tid >> 5;
         uint32_t tot;
         const uint32_t pre = block_excl_scan(packed, sm.scratch, &tot);
         const uint32_t Q = tot & 0x1FFFFu, nwords = tot >> 17;
@@ -779,13 +798,15 @@ __device__ __forceinline__ void culled_emit(Smem<false>& sm, uint32_t chunk, uin
         {
             uint32_t ord = pre & 0x1FFFFu, slot = pre >> 17;
 #pragma unroll
-            for (int f = 0; f < 6; ++f) {
+            for (int k = 0; k < 4; ++k) {
+                uint32_t wd[6];
+                const int z = 4 * w + k;
+                if (!row_words_yz(sm, y, z, wd)) continue;
+                row_words_x(sm, y, z, wd);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int y = ((w - f) & 7) + 8 * j;
-                    const uint32_t word = face_word(sm, f, y, z);
-                    if (word) P.words[slot++] = make_uint2((uint32_t)(f << 10 | y << 5 | z) | ord << 13, word);
-                    ord += __popc(word);
+                for (int f = 0; f < 6; ++f) {
+                    if (wd[f]) P.words[slot++] = make_uint2((uint32_t)(f << 10 | y << 5 | z) | ord << 13, wd[f]);
+                    ord += __popc(wd[f]);
                 }
             }
         }
@@ -832,7 +853,7 @@ __device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bo
     auto staged = [staging](uint32_t i) { return staging[i]; };
     if constexpr (!kGreedy) {
         (void)with_eq;
-        culled_emit(sm, chunk, culled_count(sm, 0, 6), out, id_of, prof);
+        culled_emit(sm, chunk, culled_count<false>(sm) + culled_count<true>(sm), out, id_of, prof);
         return;
     } else {
         // ---- greedy: sweep_log, stage_births, run_height (see above).  The log sits at the end of the
@@ -1011,11 +1032,11 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
             XPoll xp;
             halo_begin(sm, nb, n, bnd, rows, xp);
             __syncthreads();                    // +-Y / +-Z halo rows published
-            uint32_t packed = culled_count(sm, 2, 6);
+            uint32_t packed = culled_count<false>(sm);
             halo_finish(sm, voxels, nb, n, bnd, xp, prof);
             __syncthreads();                    // x halo published
             prof.mark(2);
-            packed += culled_count(sm, 0, 2);
+            packed += culled_count<true>(sm);
             culled_emit(sm, chunk, packed, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
             return;
         }
