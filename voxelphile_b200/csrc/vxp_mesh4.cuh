@@ -7,22 +7,24 @@
 //     -> occ  occupancy bit volume (bit x of word (y,z)) plus a one-voxel halo
 //     -> eq   id-equality bit volumes EX/EY/EZ, greedy only, computed from the tile for the
 //             rows that carry a visible face and held in registers until the tile is dead
-//     -> mask six face-mask sets in plane orientation (X planes through warp bit transposes)
-//     -> culled: popcount + block scan;  greedy: bit-parallel row sweep, one thread per
-//        plane, 32 constant-cost row steps (no per-quad inner loops, no divergence on
-//        quad count), finished quads staged through a shared-memory cursor
+//     -> culled: six face words per row straight from the occupancy, packed block scan, list of
+//        non-empty words shared evenly between the threads
+//     -> greedy: six face-mask sets in plane orientation (X planes through warp bit transposes),
+//        bit-parallel row sweep, one thread per plane, that only logs which runs survive each row;
+//        runs are staged and their heights resolved in parallel afterwards
 //     -> one 32-byte vertex store per quad, coalesced 8-byte index stores.
 //
 // After the equality pass the tile is dead and its 64 KiB are re-used for eq / mask /
 // staging, which is what lets three CTAs share an SM.
 //
-// Halo.  The +-X halo of a chunk is one u16 out of every 64-byte row of the neighbour:
-// 1024 sectors per face if gathered from the voxels.  Instead every CTA publishes the six
-// boundary bit planes of its own chunk (768 B, or just an "all air" / "all solid" tag) to a
+// Halo.  The +-Y / +-Z halo rows are 64-byte rows of the neighbours, fetched at kernel start.
+// The +-X halo of a chunk is one u16 out of every 64-byte row of the neighbour: 1024 sectors
+// per face if gathered from the voxels.  Instead every CTA publishes the two x-boundary bit
+// planes of its own chunk (epoch-stamped words, or just an "all air" / "all solid" tag) to a
 // context-owned scratch area as soon as its occupancy is known, and a neighbour that finds
-// the tag of the current launch reads those 128-byte planes; otherwise it gathers from the
-// voxels.  Nobody ever waits, so there is no ordering requirement between CTAs, and both
-// paths yield the same bits.
+// words of the current launch reads those planes; otherwise it gathers from the voxels.
+// Nobody ever waits, so there is no ordering requirement between CTAs, and both paths yield
+// the same bits.
 #pragma once
 #include "vxp_device.cuh"
 #include "../../include/vxp.h"
@@ -715,21 +717,6 @@ __device__ __forceinline__ void publish_range(SM& sm, uint32_t chunk, uint32_t Q
     const bool fits = f + Q <= out.cap;
     out.meta[chunk] = vxp_chunk_meta{fits ? (uint32_t)f : 0xFFFFFFFFu, Q};
     sm.first = fits ? f : ~0ull;
-}
-
-// Face word (f, y, z): bit x = face f of voxel (x,y,z) visible.  f is a compile-time constant at every call site.
-template <class SM>
-__device__ __forceinline__ uint32_t face_word(const SM& sm, int f, int y, int z) {
-    const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
-    const uint32_t c = o[0];
-    switch (f) {
-        case 0: return c & ~((c << 1) | ((sm.xh[0][z] >> y) & 1u));
-        case 1: return c & ~((c >> 1) | ((sm.xh[1][z] >> y) & 1u) << 31);
-        case 2: return c & ~o[-1];
-        case 3: return c & ~o[+1];
-        case 4: return c & ~o[-34];
-        default: return c & ~o[+34];
-    }
 }
 
 // ------------------------------------------------------------------ culled: occupancy -> quads -> buffers
