@@ -562,28 +562,31 @@ __device__ __forceinline__ uint32_t sweep_rows(const Sweep& st) {
 __device__ __forceinline__ uint32_t sweep_log(Sweep& st, uint32_t rm, uint32_t plane, uint2* entry) {
     uint32_t births = 0;
     uint32_t todo = rm | (rm << 1);
+    // the warp's trip count is known up front (no vote on the loop-carried path); the body is branch-free for
+    // lanes with rows left (predicated), so next row's loads and this row's update overlap
+    const int trips = (int)__reduce_max_sync(kFull, (uint32_t)__popc(todo));
+    int v = todo ? __ffs(todo) - 1 : 0;
     bool valid = todo != 0;
-    int v = valid ? __ffs(todo) - 1 : 0;
     todo &= todo - 1;
     uint32_t Mv = st.m[v], Hv = st.hb[v * st.hs], Vv = st.vb[v * st.vs];
-    while (__any_sync(kFull, valid)) {
+#pragma unroll 2
+    for (int it = 0; it < trips; ++it) {
         const bool validn = todo != 0;
         const int vn = validn ? __ffs(todo) - 1 : 0;
         todo &= todo - 1;
         const uint32_t Mn = st.m[vn], Hn = st.hb[vn * st.hs], Vn = st.vb[vn * st.vs];
+        // survivors of the runs alive after the previous row (C == 0: none, and then X == Es == 0 and Cs == 0)
+        const uint32_t X = st.C & Mv & Vv;
+        const uint32_t T = (X & ~st.E) + st.S;
+        const uint32_t Es = T & st.E & X;                               // end bits of the surviving runs
+        const uint32_t P = __brev(st.C) & ~__brev(st.S);
+        const uint32_t Cs = __brev((P + __brev(Es)) ^ P);               // their cover
+        const uint32_t R = Mv & ~Cs;
+        const uint32_t NS = R & ~((R << 1) & Hv);
+        const uint32_t NE = R & ~((R >> 1) & (Hv >> 1));
         if (valid) {
-            uint32_t Cs = 0;
-            if (st.C) {
-                const uint32_t X = st.C & Mv & Vv;
-                const uint32_t T = (X & ~st.E) + st.S;
-                const uint32_t Es = T & st.E & X;                       // end bits of the surviving runs
-                const uint32_t P = __brev(st.C) & ~__brev(st.S);
-                Cs = __brev((P + __brev(Es)) ^ P);                      // their cover
-            }
-            const uint32_t R = Mv & ~Cs;
-            const uint32_t NS = R & ~((R << 1) & Hv);
             st.S = (st.S & Cs) | NS;
-            st.E = (st.E & Cs) | (R & ~((R >> 1) & (Hv >> 1)));
+            st.E = (st.E & Cs) | NE;
             st.C = Mv;
             if (Mv) *entry++ = make_uint2(Cs, plane << 5 | (uint32_t)v | births << 13);
             births += __popc(NS);
