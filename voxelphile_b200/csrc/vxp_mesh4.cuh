@@ -392,7 +392,7 @@ __device__ __forceinline__ uint32_t build_masks(Smem<kGreedy>& sm, bool with_eq)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* mask = sm.tile.post.mask;
     uint32_t acc = 0;
-#pragma unroll 1
+#pragma unroll 4
     for (int k = 0; k < 4; ++k) {
         const int z = k * kWarps + warp, y = lane;
         const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
