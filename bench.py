@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--soak-seconds", type=float, default=0.3, help="minimum warm-up duration (0 under ncu)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="serialise consecutive launches (vxp_ctx_set_overlap off) in the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -267,7 +269,12 @@ def main():
         torch.cuda.synchronize()
         totals.append(int(probe.total.item()))
         counts.append(probe.meta[:, 1].cpu().numpy().astype(np.int64))
-    out = m.alloc_mesh(n_step, max(totals) + 1)
+    # two output meshes used alternately: launch k+1 may start while launch k drains (vxp_ctx_set_overlap), and a
+    # consumer would read mesh k while mesh k+1 is produced
+    outs = [m.alloc_mesh(n_step, max(totals) + 1), m.alloc_mesh(n_step, max(totals) + 1)]
+    out = outs[0]
+    overlap = not args.no_overlap and not fused
+    m.set_overlap(overlap)
     alg_bytes = [algorithmic_bytes(c) if not fused else 12 * n_step + 56 * int(c.sum()) + 8 * n_step for c in counts]
 
     # ---------------- warm-up (>= W steps and >= 0.3 s so clocks have ramped)
@@ -276,7 +283,7 @@ def main():
     t_w = time.time()
     k = 0
     while k < args.warmup or time.time() - t_w < args.soak_seconds:
-        launch(k, out)
+        launch(k, outs[k % 2])
         k += 1
         if k % 64 == 0:
             torch.cuda.synchronize()
@@ -285,22 +292,15 @@ def main():
     _ = gather_counts(out.meta[:, 1].to(torch.int64), n_step * world if not fused else coords_np.shape[0], rank, world)
     barrier()
 
-    # ---------------- timed region: exactly K steps, per-launch events on the launching stream
+    # ---------------- timed region: exactly K steps, back to back on the launching stream, device-timed
     launches0 = m.launches
-    # every EV_EVERY-th launch is bracketed by its own pair of events (an event record costs ~2.7 us of stream
-    # time, measured with tools/loop_overhead.py, so bracketing all of them would slow the loop by 5 %)
-    EV_EVERY = 1 if args.steps <= 64 else 7           # 7 is coprime to the 4 rotating batches
-    ev = {s: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for s in range(0, args.steps, EV_EVERY)}
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start, e_kend, e_end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t0 = time.time()
     e_start.record()
     for s in range(args.steps):
-        if s in ev:
-            ev[s][0].record()
-        launch(s, out)
-        if s in ev:
-            ev[s][1].record()
+        launch(s, outs[s % 2])
+    e_kend.record()
+    out = outs[(args.steps - 1) % 2]
     # the one collective of the path: final host gather of mesh sizes (per-chunk quad counts)
     final_counts = gather_counts(out.meta[:, 1].to(torch.int64), n_step * world, rank, world) if not fused else \
         gather_counts(out.meta[:, 1].to(torch.int64), coords_np.shape[0], rank, world)
@@ -313,15 +313,27 @@ def main():
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
     ms_per_step = elapsed_ms / args.steps
-    kernel_steps = sorted(ev)
-    kernel_ms = [ev[s][0].elapsed_time(ev[s][1]) for s in kernel_steps]
     clocks = sampler.stop(t0, t1, "timed region")
     units_per_step = n_step * world if not fused else coords_np.shape[0]
     value = units_per_step / (ms_per_step * 1e-3)
 
-    # roofline of the dominant (only) kernel: algorithmic bytes / mean launch duration
-    mean_ms = statistics.mean(kernel_ms)
-    mean_bytes = statistics.mean(alg_bytes[s % len(batches)] for s in kernel_steps)
+    # roofline of the dominant (only) kernel: algorithmic bytes per launch / average launch duration over the timed
+    # region (events around the K launches, gather excluded).  With overlap on, consecutive launches share the GPU
+    # for the length of a tail, so the average duration is the launch-to-launch period; the duration of a launch
+    # that has the GPU to itself is measured separately below (overlap off, every launch between its own events).
+    mean_ms = e_start.elapsed_time(e_kend) / args.steps
+    mean_bytes = statistics.mean(alg_bytes[s % len(batches)] for s in range(args.steps))
+    m.set_overlap(False)
+    iso_n = min(args.steps, 140)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iso_n)]
+    for s in range(iso_n):
+        ev[s][0].record()
+        launch(s, outs[s % 2])
+        ev[s][1].record()
+    torch.cuda.synchronize()
+    m.set_overlap(overlap)
+    iso_ms = [a.elapsed_time(b) for a, b in ev]
+    iso_bytes = statistics.mean(alg_bytes[s % len(batches)] for s in range(iso_n))
     peak, peak_src = hbm_peak()
     achieved = mean_bytes / (mean_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
@@ -329,10 +341,13 @@ def main():
     ncu_traffic = {"terrain_culled": 272.6e6 + 74.1e6, "terrain_greedy": 273.3e6 + 28.1e6}.get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic, "peak_source": peak_src, "kernel": "mesh_kernel" if not fused else "terrain_mesh_kernel",
-                "kernel_ms_mean": mean_ms, "kernel_ms_min": min(kernel_ms),
-                "algorithmic_bytes_per_launch": mean_bytes,
-                "launches_timed": len(kernel_ms),
-                "note": "event bracket = 8-byte counter memset + kernel"}
+                "kernel_ms_mean": mean_ms, "algorithmic_bytes_per_launch": mean_bytes, "launches_timed": args.steps,
+                "overlap": overlap,
+                "isolated": {"kernel_ms_mean": statistics.mean(iso_ms), "kernel_ms_min": min(iso_ms), "launches": iso_n,
+                             "achieved": iso_bytes / (statistics.mean(iso_ms) * 1e-3) / 1e9,
+                             "frac": iso_bytes / (statistics.mean(iso_ms) * 1e-3) / 1e9 / peak,
+                             "note": "overlap off, each launch between its own pair of events"},
+                "note": "kernel_ms_mean = (events around the K back-to-back launches) / K; no memset, no other kernel"}
 
     # ---------------- e2e: host buffers in, host mesh out, through vxp_mesh_chunks_host / vxp_terrain_mesh_host
     e2e = None
@@ -393,17 +408,23 @@ def main():
 
         other = GREEDY if mode == CULLED else CULLED
         oprobe = m.alloc_mesh(n_step, 0)
+        m.set_overlap(False)
         ocounts = []
         for k in range(len(batches)):
             m.mesh(batches[k], dnbr, other, out=oprobe)
             torch.cuda.synchronize()
             ocounts.append(oprobe.meta[:, 1].cpu().numpy().astype(np.int64))
-        oout = m.alloc_mesh(n_step, max(int(c.sum()) for c in ocounts) + 1)
-        ms = timed(lambda s: m.mesh(batches[s % len(batches)], dnbr, other, out=oout))
+        oouts = [m.alloc_mesh(n_step, max(int(c.sum()) for c in ocounts) + 1) for _ in range(2)]
+        ms_iso = timed(lambda s: m.mesh(batches[s % len(batches)], dnbr, other, out=oouts[s % 2]))
+        m.set_overlap(overlap)
+        ms = timed(lambda s: m.mesh(batches[s % len(batches)], dnbr, other, out=oouts[s % 2]), steps=200)
+        m.set_overlap(False)
         ob = statistics.mean(algorithmic_bytes(c) for c in ocounts)
         also["greedy" if other == GREEDY else "culled"] = {
             "chunks_per_s": n_step / (ms * 1e-3), "ms_per_step": ms, "hbm_gbs": ob / (ms * 1e-3) / 1e9,
-            "frac": ob / (ms * 1e-3) / 1e9 / peak, "quads_per_batch": float(np.mean([c.sum() for c in ocounts]))}
+            "frac": ob / (ms * 1e-3) / 1e9 / peak, "overlap": overlap, "ms_per_step_serialised": ms_iso,
+            "frac_serialised": ob / (ms_iso * 1e-3) / 1e9 / peak,
+            "quads_per_batch": float(np.mean([c.sum() for c in ocounts]))}
         # the same workload with two batches in flight (two contexts, two streams): the tail of one launch and the
         # ramp of the next overlap, which a single in-order stream cannot do
         m2 = Mesher(local)

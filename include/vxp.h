@@ -56,7 +56,7 @@ typedef struct vxp_mesh_dev {
     uint64_t *verts;          /* 4 * capacity_quads vertices, 8 B each        */
     uint32_t *indices;        /* 6 * capacity_quads indices                    */
     vxp_chunk_meta *meta;     /* n entries                                     */
-    uint64_t *total_quads;    /* one counter; zeroed by the call               */
+    uint64_t *total_quads;    /* one counter; written by the call (need not be zeroed) */
     uint64_t capacity_quads;
 } vxp_mesh_dev;
 
@@ -77,6 +77,17 @@ void vxp_ctx_destroy(vxp_ctx *ctx);
  * vxp_ctx_reset_stream returns to the context's own non-blocking stream. */
 vxp_status vxp_ctx_set_stream(vxp_ctx *ctx, void *cuda_stream);
 vxp_status vxp_ctx_reset_stream(vxp_ctx *ctx);
+/* Launch overlap (off by default).  When enabled, a vxp_mesh_batch call may start executing while the previous
+ * vxp_mesh_batch call on the same context and stream is still finishing (programmatic dependent launch): the
+ * next batch's chunks fill the SMs that the tail of the previous batch leaves idle.  At most two calls are ever
+ * in flight; call k+2 never starts before call k has completed.  The caller promises, while it is enabled:
+ *   - consecutive vxp_mesh_batch calls use disjoint output arrays (verts, indices, meta, total_quads), e.g.
+ *     two vxp_mesh_dev used alternately; the arrays of call k may be re-used by call k+2;
+ *   - the voxels and neighbour table of a call were complete before the PREVIOUS vxp_mesh_batch call was
+ *     enqueued (a call that follows any other vxp call, vxp_ctx_synchronize or vxp_ctx_set_overlap never
+ *     starts early, so freshly produced inputs are safe behind one of those).
+ * Results are identical either way. */
+vxp_status vxp_ctx_set_overlap(vxp_ctx *ctx, int enabled);
 vxp_status vxp_ctx_synchronize(vxp_ctx *ctx);
 const char *vxp_status_str(vxp_status s);
 /* Detail of the last VXP_ERR_CUDA on this context ("" if none). */

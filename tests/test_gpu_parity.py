@@ -365,3 +365,57 @@ def test_host_pipeline_with_halo_chunks(mesher):
     assert sh.n_owned >= 256 and len(sh.batch_index) > sh.n_owned
     assert np.array_equal(host.meta[:, 1], want_cnt[:sh.n_owned])
     assert np.array_equal(_chunk_hashes(host), want_hash[:sh.n_owned])
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_overlapped_launches(mode, mname):
+    """vxp_ctx_set_overlap: a stream of back-to-back mesh calls over four different full-size batches, two
+    output meshes used alternately, gives every call the result of the same call made alone (per-chunk counts,
+    ranges and key hashes vs the oracle for one batch; bit-identical per-chunk hashes vs serial for all)."""
+    import torch
+    from voxelphile_b200 import Mesher, grid_coords, neighbour_table
+    m = Mesher(0)
+    m.use_current_torch_stream()
+    try:
+        coords = grid_coords((0, 0, 0), (16, 16, 16))
+        nbr = neighbour_table(coords)
+        dn = dev(nbr)
+        batches = [m.terrain_fill(dev(coords), 42 + k) for k in range(4)]
+        serial = []
+        for b in batches:
+            o = m.mesh(b, dn, mode, capacity=4096 * 700)
+            torch.cuda.synchronize()
+            h = o.to_host()
+            serial.append((h.total_quads, h.meta[:, 1].copy(), _chunk_hashes(h)))
+        vox0 = batches[0].cpu().numpy().view(np.uint16)
+        want_hash, want_cnt = O.mesh_batch_hash(vox0, nbr, mode)
+        assert np.array_equal(serial[0][1], want_cnt) and np.array_equal(serial[0][2], want_hash)
+        outs = [m.alloc_mesh(4096, 4096 * 700), m.alloc_mesh(4096, 4096 * 700)]
+        m.set_overlap(True)
+        torch.cuda.synchronize()
+        for r in range(8):
+            # 2r+1 calls in a row, then look at the last two (still intact: call k+2 is what re-uses call k's arrays)
+            k_last = 2 * r + 1
+            for k in range(k_last + 1):
+                m.mesh(batches[(k + r) % 4], dn, mode, out=outs[k % 2])
+            torch.cuda.synchronize()
+            for k in (k_last - 1, k_last):
+                h = outs[k % 2].to_host()
+                tq, cnt, hs = serial[(k + r) % 4]
+                assert h.total_quads == tq, (r, k)
+                assert np.array_equal(h.meta[:, 1], cnt), (r, k)
+                assert np.array_equal(_chunk_hashes(h), hs), (r, k)
+                order = np.argsort(h.meta[:, 0][cnt > 0])
+                f, c = h.meta[:, 0][cnt > 0][order].astype(np.int64), cnt[cnt > 0][order].astype(np.int64)
+                assert f[0] == 0 and np.array_equal(f[1:], np.cumsum(c)[:-1]), "ranges must tile [0, Q)"
+        # modes and other calls may be mixed freely: a fill between two calls serialises them
+        other = 1 - mode
+        o1 = m.mesh(batches[1], dn, other, out=outs[0])
+        scratch = m.terrain_fill(dev(coords), 42)
+        o2 = m.mesh(scratch, dn, mode, out=outs[1])
+        torch.cuda.synchronize()
+        h2 = o2.to_host()
+        assert h2.total_quads == serial[0][0] and np.array_equal(_chunk_hashes(h2), serial[0][2])
+        m.set_overlap(False)
+    finally:
+        m.close()

@@ -42,6 +42,7 @@ SIGNATURES = {
     "vxp_ctx_destroy": (None, [C.c_void_p]),
     "vxp_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxp_ctx_reset_stream": (C.c_int, [C.c_void_p]),
+    "vxp_ctx_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "vxp_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "vxp_status_str": (C.c_char_p, [C.c_int]),
     "vxp_last_error": (C.c_char_p, [C.c_void_p]),

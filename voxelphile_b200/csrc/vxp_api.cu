@@ -27,8 +27,16 @@ struct vxp_ctx {
     uint64_t* d_verts = nullptr;    uint32_t* d_indices = nullptr; size_t quads_cap = 0;
     uint64_t* d_total = nullptr;
     // boundary-summary scratch of the mesh kernel (vxp_launch.h: BoundaryScratch)
-    uint32_t* d_tags = nullptr;     unsigned long long* d_planes = nullptr;  size_t bnd_cap = 0;   // chunks
+    // Two launch slots used alternately, so that consecutive launches share nothing (launch chaining, vxp_mesh4.cuh).
+    uint32_t* d_tags[2] = {};       unsigned long long* d_planes[2] = {};    size_t bnd_cap = 0;   // chunks
     uint32_t epoch = 0;
+    unsigned long long* d_counters = nullptr;   // one zero-initialised launch counter per slot
+    int slot = 0;
+    int overlap = 0;                            // vxp_ctx_set_overlap
+    bool launched = false;                      // a mesh launch has been enqueued ...
+    cudaStream_t launch_stream = nullptr;       // ... on this stream
+    bool chain_open = false;                    // ... with overlap enabled, and nothing else of ours since
+    cudaEvent_t ev_chain = nullptr;
     // column scratch of the fused terrain+mesh path (vxp_launch.h: ColumnScratch)
     unsigned char* d_columns = nullptr;  size_t columns_cap = 0;   // chunks
     vxp::ColumnScratch columns{};
@@ -119,29 +127,63 @@ vxp_status grow_host_quads(vxp_ctx* ctx, size_t need) {
     return VXP_OK;
 }
 
-// Scratch for one mesh launch over n chunks: grown on demand (cudaFree synchronises with any launch
-// still using the old area), tags zeroed on allocation and when the 30-bit epoch wraps.
+// Scratch for one mesh launch over n chunks, in the slot the launch will use: grown on demand (cudaFree
+// synchronises with any launch still using the old area), zeroed on allocation and when the 30-bit epoch wraps.
 vxp_status next_boundary_scratch(vxp_ctx* ctx, uint32_t n, vxp::BoundaryScratch* out) {
     if (n > ctx->bnd_cap) {
         const size_t want = (size_t)n + n / 4;
-        if (ctx->d_tags) VXP_CUDA(ctx, cudaFree(ctx->d_tags));
-        if (ctx->d_planes) VXP_CUDA(ctx, cudaFree(ctx->d_planes));
-        ctx->d_tags = nullptr;
-        ctx->d_planes = nullptr;
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->d_tags[k]) VXP_CUDA(ctx, cudaFree(ctx->d_tags[k]));
+            if (ctx->d_planes[k]) VXP_CUDA(ctx, cudaFree(ctx->d_planes[k]));
+            ctx->d_tags[k] = nullptr;
+            ctx->d_planes[k] = nullptr;
+        }
         ctx->bnd_cap = 0;
-        VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_tags), vxp::boundary_tag_bytes((uint32_t)want)));
-        VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_planes), vxp::boundary_plane_bytes((uint32_t)want)));
-        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_tags, 0, vxp::boundary_tag_bytes((uint32_t)want), ctx->stream));
-        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_planes, 0, vxp::boundary_plane_bytes((uint32_t)want), ctx->stream));
+        for (int k = 0; k < 2; ++k) {
+            VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_tags[k]), vxp::boundary_tag_bytes((uint32_t)want)));
+            VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_planes[k]), vxp::boundary_plane_bytes((uint32_t)want)));
+            VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_tags[k], 0, vxp::boundary_tag_bytes((uint32_t)want), ctx->stream));
+            VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_planes[k], 0, vxp::boundary_plane_bytes((uint32_t)want), ctx->stream));
+        }
         ctx->bnd_cap = want;
         ctx->epoch = 0;
     }
     if (++ctx->epoch >= (1u << 30)) {
-        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_tags, 0, vxp::boundary_tag_bytes((uint32_t)ctx->bnd_cap), ctx->stream));
-        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_planes, 0, vxp::boundary_plane_bytes((uint32_t)ctx->bnd_cap), ctx->stream));
+        for (int k = 0; k < 2; ++k) {
+            VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_tags[k], 0, vxp::boundary_tag_bytes((uint32_t)ctx->bnd_cap), ctx->stream));
+            VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_planes[k], 0, vxp::boundary_plane_bytes((uint32_t)ctx->bnd_cap), ctx->stream));
+        }
         ctx->epoch = 1;
     }
-    *out = vxp::BoundaryScratch{ctx->d_tags, ctx->d_planes, ctx->epoch};
+    *out = vxp::BoundaryScratch{ctx->d_tags[ctx->slot], ctx->d_planes[ctx->slot], ctx->epoch};
+    return VXP_OK;
+}
+
+// One whole-batch mesh launch in the context's next slot.  Launches of one context are chained on one stream
+// (the chain's guarantees hold per stream): if the caller has switched streams since the last launch, the new
+// stream first waits for the old one.
+vxp_status chained_mesh_launch(vxp_ctx* ctx, const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, int greedy,
+                               const vxp_mesh_dev& dev) {
+    vxp::BoundaryScratch scratch{nullptr, nullptr, 0};
+    if (n) {
+        const vxp_status s = next_boundary_scratch(ctx, n, &scratch);
+        if (s != VXP_OK) return s;
+        if (ctx->launched && ctx->launch_stream != ctx->stream) {
+            VXP_CUDA(ctx, cudaEventRecord(ctx->ev_chain, ctx->launch_stream));
+            VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0));
+        }
+    }
+    // the launch may start early only behind another overlapping mesh launch of this context on this stream: after
+    // anything else of ours (fills, fused and host-level calls) it serialises as usual
+    const int early = ctx->overlap && ctx->chain_open && ctx->launch_stream == ctx->stream;
+    VXP_CUDA(ctx, vxp::launch_mesh(d_voxels, d_nbr6, n, greedy, dev, scratch, ctx->d_counters + ctx->slot, early, ctx->stream));
+    if (n) {
+        ctx->launches += 1;
+        ctx->slot ^= 1;
+        ctx->launched = true;
+        ctx->launch_stream = ctx->stream;
+        ctx->chain_open = ctx->overlap != 0;
+    }
     return VXP_OK;
 }
 
@@ -192,8 +234,7 @@ vxp_status mesh_into_host(vxp_ctx* ctx, uint32_t n, Launch launch, vxp_mesh_host
     uint64_t total = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
         vxp_mesh_dev dev{ctx->d_verts, ctx->d_indices, ctx->d_meta, ctx->d_total, ctx->quads_cap};
-        VXP_CUDA(ctx, launch(dev));
-        ctx->launches += n ? 1 : 0;
+        VXP_CUDA(ctx, launch(dev));   // counts itself in ctx->launches
         VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_total, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                       ctx->stream));
         VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -213,6 +254,7 @@ vxp_status mesh_into_host(vxp_ctx* ctx, uint32_t n, Launch launch, vxp_mesh_host
                                       cudaMemcpyDeviceToHost, ctx->stream));
     }
     VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->chain_open = false;
     out->verts = ctx->h_verts;
     out->indices = ctx->h_indices;
     out->meta = ctx->h_meta;
@@ -258,6 +300,9 @@ vxp_status vxp_ctx_create(int device, vxp_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = vxp::configure_device();
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_total), sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_total), sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_totals), vxp_ctx::kMaxSlices * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
@@ -289,8 +334,12 @@ void vxp_ctx_destroy(vxp_ctx* ctx) {
     cudaFree(ctx->d_indices);
     cudaFree(ctx->d_total);
     cudaFree(ctx->d_columns);
-    cudaFree(ctx->d_tags);
-    cudaFree(ctx->d_planes);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(ctx->d_tags[k]);
+        cudaFree(ctx->d_planes[k]);
+    }
+    cudaFree(ctx->d_counters);
+    if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     cudaFreeHost(ctx->h_meta);
     cudaFreeHost(ctx->h_verts);
     cudaFreeHost(ctx->h_indices);
@@ -319,10 +368,18 @@ vxp_status vxp_ctx_reset_stream(vxp_ctx* ctx) {
     return VXP_OK;
 }
 
+vxp_status vxp_ctx_set_overlap(vxp_ctx* ctx, int enabled) {
+    if (!ctx) return VXP_ERR_BAD_ARG;
+    ctx->overlap = enabled ? 1 : 0;
+    ctx->chain_open = false;
+    return VXP_OK;
+}
+
 vxp_status vxp_ctx_synchronize(vxp_ctx* ctx) {
     if (!ctx) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->chain_open = false;
     return VXP_OK;
 }
 
@@ -378,6 +435,7 @@ vxp_status vxp_terrain_fill_batch(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
                                   uint16_t* d_voxels) {
     if (!ctx || (n && (!d_coords || !d_voxels)) || !aligned16(d_voxels)) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
+    ctx->chain_open = false;
     VXP_CUDA(ctx, vxp::launch_terrain_fill(d_coords, n, seed, d_voxels, ctx->stream));
     ctx->launches += n ? 1 : 0;
     return VXP_OK;
@@ -388,6 +446,7 @@ vxp_status vxp_pattern_fill_batch(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
     if (!ctx || (n && (!d_coords || !d_voxels)) || !aligned16(d_voxels)) return VXP_ERR_BAD_ARG;
     if (pattern != VXP_PATTERN_CHECKER && pattern != VXP_PATTERN_SOLID4) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
+    ctx->chain_open = false;
     VXP_CUDA(ctx, vxp::launch_pattern_fill(d_coords, n, (int)pattern, d_voxels, ctx->stream));
     ctx->launches += n ? 1 : 0;
     return VXP_OK;
@@ -398,14 +457,7 @@ vxp_status vxp_mesh_batch(vxp_ctx* ctx, const uint16_t* d_voxels, const int32_t*
     if (!ctx || !valid_mode(mode) || !valid_out(out, n)) return VXP_ERR_BAD_ARG;
     if (n && (!d_voxels || !aligned16(d_voxels))) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
-    vxp::BoundaryScratch scratch{nullptr, nullptr, 0};
-    if (n) {
-        const vxp_status s = next_boundary_scratch(ctx, n, &scratch);
-        if (s != VXP_OK) return s;
-    }
-    VXP_CUDA(ctx, vxp::launch_mesh(d_voxels, d_nbr6, n, mode == VXP_MODE_GREEDY, *out, scratch, ctx->stream));
-    ctx->launches += n ? 1 : 0;
-    return VXP_OK;
+    return chained_mesh_launch(ctx, d_voxels, d_nbr6, n, mode == VXP_MODE_GREEDY, *out);
 }
 
 vxp_status vxp_terrain_mesh_fused(vxp_ctx* ctx, const vxp_coord* d_coords, uint32_t n, uint64_t seed,
@@ -417,6 +469,7 @@ vxp_status vxp_terrain_mesh_fused(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
         const vxp_status s = column_scratch(ctx, n, &cols);
         if (s != VXP_OK) return s;
     }
+    ctx->chain_open = false;
     VXP_CUDA(ctx, vxp::launch_terrain_mesh(d_coords, n, seed, mode == VXP_MODE_GREEDY, *out, cols, ctx->stream));
     ctx->launches += n ? 1 : 0;
     return VXP_OK;
@@ -432,6 +485,7 @@ vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
     vxp_status s;
     if ((s = grow_device(ctx, &ctx->d_coords, &ctx->coords_cap, n, 1)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
+    ctx->chain_open = false;
     VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_coords, coords, (size_t)n * sizeof(vxp_coord), cudaMemcpyHostToDevice,
                                   ctx->stream));
     VXP_CUDA(ctx, vxp::launch_terrain_fill(ctx->d_coords, n, seed, ctx->d_voxels, ctx->stream));
@@ -482,6 +536,13 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
         }
         vxp::BoundaryScratch scratch{nullptr, nullptr, 0};
         if ((s = next_boundary_scratch(ctx, n, &scratch)) != VXP_OK) return s;
+        if (ctx->launched && ctx->launch_stream != ctx->stream) {
+            VXP_CUDA(ctx, cudaEventRecord(ctx->ev_chain, ctx->launch_stream));
+            VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0));
+        }
+        ctx->launched = true;
+        ctx->launch_stream = ctx->stream;
+        ctx->chain_open = false;
         const vxp_mesh_dev dev{ctx->d_verts, ctx->d_indices, ctx->d_meta, ctx->d_total, ctx->quads_cap};
         // uploads: neighbour table and read-only halo chunks first, then the slices in order
         VXP_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
@@ -544,9 +605,7 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
     return mesh_into_host(
         ctx, n,
         [&](const vxp_mesh_dev& dev) {
-            vxp::BoundaryScratch scratch{nullptr, nullptr, 0};
-            if (next_boundary_scratch(ctx, n, &scratch) != VXP_OK) return cudaErrorMemoryAllocation;
-            return vxp::launch_mesh(ctx->d_voxels, d_nbr, n, greedy, dev, scratch, ctx->stream);
+            return chained_mesh_launch(ctx, ctx->d_voxels, d_nbr, n, greedy, dev) == VXP_OK ? cudaSuccess : cudaErrorUnknown;
         },
         out);
 }
@@ -565,6 +624,7 @@ vxp_status vxp_terrain_mesh_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
         [&](const vxp_mesh_dev& dev) {
             vxp::ColumnScratch cols{};
             if (n && column_scratch(ctx, n, &cols) != VXP_OK) return cudaErrorMemoryAllocation;
+            ctx->launches += n ? 1 : 0;
             return vxp::launch_terrain_mesh(ctx->d_coords, n, seed, mode == VXP_MODE_GREEDY, dev, cols, ctx->stream);
         },
         out);

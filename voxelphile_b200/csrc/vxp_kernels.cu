@@ -285,7 +285,24 @@ cudaError_t launch_pattern_fill(const vxp_coord* d_coords, uint32_t n, int patte
 
 static v4::MeshOut mesh_out(const vxp_mesh_dev& o) {
     return v4::MeshOut{reinterpret_cast<unsigned long long*>(o.verts), o.indices, o.meta,
-                       reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads};
+                       reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads, 0ull};
+}
+
+template <bool kGreedy>
+static cudaError_t launch_mesh_kernel(uint32_t grid, int overlap, cudaStream_t stream, const uint16_t* d_voxels,
+                                      const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi, v4::MeshOut out, v4::Bnd bnd,
+                                      v4::Chain chain) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = sizeof(v4::Smem<kGreedy>);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, v4::mesh_kernel<kGreedy>, d_voxels, d_nbr6, n, lo, hi, out, bnd, chain);
 }
 
 cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi,
@@ -294,18 +311,23 @@ cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, u
     if (lo >= hi) return cudaSuccess;
     const v4::Bnd bnd{scratch.tags, scratch.planes, scratch.epoch};
     const uint32_t grid = hi - lo;
-    if (greedy)
-        v4::mesh_kernel<true><<<grid, kThreads, sizeof(v4::Smem<true>), stream>>>(d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd);
-    else
-        v4::mesh_kernel<false><<<grid, kThreads, sizeof(v4::Smem<false>), stream>>>(d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd);
-    return cudaGetLastError();
+    const v4::Chain chain{nullptr};
+    return greedy ? launch_mesh_kernel<true>(grid, 0, stream, d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd, chain)
+                  : launch_mesh_kernel<false>(grid, 0, stream, d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd, chain);
 }
 
 cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, int greedy,
-                        const vxp_mesh_dev& o, const BoundaryScratch& scratch, cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
-    if (e != cudaSuccess || n == 0) return e;
-    return launch_mesh_range(d_voxels, d_nbr6, n, 0, n, greedy, o, scratch, stream);
+                        const vxp_mesh_dev& o, const BoundaryScratch& scratch, unsigned long long* counter, int overlap,
+                        cudaStream_t stream) {
+    if (n == 0) return cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
+    if (n > (1u << 22) - 1u) return cudaErrorInvalidValue;   // CTA count field of the launch counter
+    const v4::Bnd bnd{scratch.tags, scratch.planes, scratch.epoch};
+    v4::MeshOut out = mesh_out(o);
+    out.total = counter;
+    out.cta_inc = v4::kCtaOne;
+    const v4::Chain chain{reinterpret_cast<unsigned long long*>(o.total_quads)};
+    return greedy ? launch_mesh_kernel<true>(n, overlap, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain)
+                  : launch_mesh_kernel<false>(n, overlap, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain);
 }
 
 size_t boundary_tag_bytes(uint32_t n) { return (size_t)n * sizeof(uint32_t); }

@@ -40,8 +40,14 @@ cudaError_t launch_terrain_fill(const vxp_coord* d_coords, uint32_t n, uint64_t 
                                 cudaStream_t stream);
 cudaError_t launch_pattern_fill(const vxp_coord* d_coords, uint32_t n, int pattern, uint16_t* d_voxels,
                                 cudaStream_t stream);
+// One whole-batch launch.  `counter` is a context-owned, zero-initialised 8-byte launch counter (vxp_mesh4.cuh,
+// "launch chaining"): the kernel reserves quad ranges from it, hands the total to *out.total_quads and leaves it
+// zeroed, so no memset precedes the kernel.  overlap != 0 launches with programmatic stream serialisation: the
+// kernel may start while the previous mesh launch on the stream is still draining.  The caller must then alternate
+// between two counters / scratch areas / output arrays.
 cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, int greedy,
-                        const vxp_mesh_dev& out, const BoundaryScratch& scratch, cudaStream_t stream);
+                        const vxp_mesh_dev& out, const BoundaryScratch& scratch, unsigned long long* counter, int overlap,
+                        cudaStream_t stream);
 // chunks [lo, hi) of a batch of n; does NOT zero *out.total_quads (ranges of one batch accumulate into it)
 cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi,
                               int greedy, const vxp_mesh_dev& out, const BoundaryScratch& scratch, cudaStream_t stream);

@@ -132,6 +132,7 @@ struct __align__(128) Smem {
     uint32_t rows[192];         // greedy: visited rows of each plane
     uint32_t first_run[192];    // greedy: ordinal of the first run of each plane
     uint32_t cursor;            // staging fill level
+    uint32_t counted;           // thread 0 only: this CTA has checked in at the launch counter (reserve_quads)
     uint32_t ones;              // 0xFFFFFFFF: stand-in equality row for single-id chunks
     unsigned long long first;
     unsigned long long mbar[kSlabs];
@@ -139,13 +140,27 @@ struct __align__(128) Smem {
 static_assert(sizeof(Post<false>) <= kTileBytes && sizeof(Post<true>) <= kTileBytes, "post-tile layout overflows the tile");
 static_assert(3 * (sizeof(Smem<true>) + 1024) <= 227 * 1024 + 1024, "three CTAs per SM need <= ~75 KiB each");
 
+// Quad counter of a launch.  Low kQuadBits bits: quads reserved so far (a chunk's atomic add returns the
+// first quad of its range); the bits above count the CTAs that have checked in (MeshOut::cta_inc = kCtaOne;
+// 0 when nobody waits for the count: fused path, ranges of the sliced host pipeline).  One word, so the
+// check-in of a chunk with quads rides on the reservation it performs anyway and needs no ordering of its own.
+constexpr int kQuadBits = 42;                                 // 98 304 quads x 2.9 M chunks (180 GB of voxels) < 2^42
+constexpr unsigned long long kQuadMask = (1ull << kQuadBits) - 1ull;
+constexpr unsigned long long kCtaOne = 1ull << kQuadBits;     // at most 2^22 CTAs per launch
 struct MeshOut {
     unsigned long long* verts;
     uint32_t* indices;
     vxp_chunk_meta* meta;
-    unsigned long long* total;
+    unsigned long long* total;     // the counter the chunks reserve from (context-owned slot, or the caller's total_quads)
     unsigned long long cap;
+    unsigned long long cta_inc;    // kCtaOne: every CTA checks in exactly once (mesh_kernel); 0: plain quad counter
 };
+// Reserve Q quads (and check the CTA in); returns the first quad of the range.  Thread 0 only.
+template <class SM>
+__device__ __forceinline__ unsigned long long reserve_quads(SM& sm, const MeshOut& out, uint32_t Q) {
+    sm.counted = 1u;
+    return atomicAdd(out.total, (unsigned long long)Q + out.cta_inc) & kQuadMask;
+}
 
 // 8 consecutive u16 -> 8 bits (bit j = element j non-zero): 4 VIMNMX.U16x2 + 3 LEA + 2 logic
 __device__ __forceinline__ uint32_t nz8(uint4 q) {
@@ -784,7 +799,7 @@ __device__ __forceinline__ void culled_emit(Smem<false>& sm, uint32_t chunk, uin
         }
         prof.count(11);
         unsigned long long fq = 0;
-        if (tid == 0) fq = atomicAdd(out.total, (unsigned long long)Q);   // in flight while the records are staged
+        if (tid == 0) fq = reserve_quads(sm, out, Q);   // in flight while the records are staged
         {
             uint32_t ord = pre & 0x1FFFFu, slot = pre >> 17;
 #pragma unroll
@@ -876,7 +891,7 @@ __device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bo
 #endif
             const uint32_t first_run = block_excl_scan(births, sm.scratch, &Q);   // barriers: log published
             if (tid < 192) sm.first_run[tid] = first_run;
-            if (tid == 0) f = atomicAdd(out.total, (unsigned long long)Q);       // in flight while the records are staged
+            if (tid == 0) f = reserve_quads(sm, out, Q);       // in flight while the records are staged
             prof.mark(5);
             const uint32_t cap_small = kCap - 2 * nL, cap_arena = Post<true>::kArena - 2 * nL;
             if (Q <= cap_arena) {                         // block-uniform
@@ -898,7 +913,7 @@ __device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bo
             }
             __syncthreads();
             Q = sm.cursor;
-            if (tid == 0) f = atomicAdd(out.total, (unsigned long long)Q);
+            if (tid == 0) f = reserve_quads(sm, out, Q);
         }
         auto publish = [&] { if (tid == 0) publish_range(sm, chunk, Q, f, out); };
         prof.count(14);
@@ -1045,31 +1060,63 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
     mesh_tail<kGreedy>(sm, chunk, fl, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
 }
 
+// ---- launch chaining.  Consecutive mesh launches of a context may overlap on the device (programmatic
+// dependent launch): every CTA lets the next launch start as soon as it is resident itself, so the next
+// launch's CTAs fill the slots that the tail of this one leaves empty.  What makes that safe:
+//   * launches alternate between two context-owned slots (counter + boundary scratch), so launch k+1 shares
+//     nothing with launch k (the caller alternates the output arrays, see vxp_ctx_set_overlap);
+//   * the LAST CTA of every launch waits for the previous launch to complete before it lets the next one
+//     start, so launch k+2 - which re-uses the slot of launch k - can never begin before k has completed;
+//   * the same CTA closes the launch: it waits until every CTA has checked in at the slot counter, hands the
+//     quad total to the caller's total_quads and leaves the slot zeroed for launch k+2.  Nobody else waits.
+// Without the launch attribute (the default) both instructions are no-ops and launches serialise as usual.
+struct Chain {
+    unsigned long long* user_total;   // the caller's total_quads; nullptr: no check-in, no hand-over (MeshOut::cta_inc == 0)
+};
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Meshes chunks [chunk0, hi) of a batch of n, one chunk per CTA (grid = hi - chunk0): the hardware block
 // scheduler is the load balancer.  (Persistent CTAs drawing tickets were measured 7-12 % slower: a CTA
 // that draws its next chunk early delays that chunk's boundary planes for the neighbours that poll them.)
 template <bool kGreedy>
 __global__ void __launch_bounds__(kThreads, 3)
 mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, uint32_t chunk0, uint32_t hi,
-            MeshOut out, Bnd bnd) {
+            MeshOut out, Bnd bnd, Chain chain) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<kGreedy>& sm = *reinterpret_cast<Smem<kGreedy>*>(smem_raw);
     const uint32_t chunk = chunk0 + blockIdx.x;
-    if (chunk >= hi) return;
+    const bool closer = chain.user_total != nullptr && blockIdx.x == gridDim.x - 1;
     if (threadIdx.x == 0) {
+        if (closer) griddep_wait();             // the previous launch has completed (its slot is free for the next one)
         sm.ones = kFull;
+        sm.counted = 0u;
 #pragma unroll
         for (int s = 0; s < kSlabs; ++s) mbar_init(&sm.mbar[s], 1);
         fence_mbar_init();
     }
     __syncthreads();                            // barrier init visible to all
+    griddep_launch_dependents();
 #ifdef VXP_PROFILE
     if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][0] = prof_now();
 #endif
-    mesh_chunk(sm, voxels, nbr6, n, chunk, 0u, out, bnd);
+    if (chunk < hi) mesh_chunk(sm, voxels, nbr6, n, chunk, 0u, out, bnd);
 #ifdef VXP_PROFILE
     if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][1] = prof_now();
 #endif
+    if (threadIdx.x == 0 && chain.user_total != nullptr) {
+        if (!sm.counted) red_add_u64(out.total, kCtaOne);          // a chunk without quads checks in here
+        if (closer) {
+            // sm.counted: this CTA's own reservation has returned, so the counter already includes it
+            unsigned long long t;
+            while (((t = ld_relaxed_u64(out.total)) >> kQuadBits) != gridDim.x) __nanosleep(64);
+            *chain.user_total = t & kQuadMask;
+            st_relaxed_u64(out.total, 0ull);    // nobody adds any more: every CTA has checked in
+        }
+    }
 }
 
 } // namespace v4

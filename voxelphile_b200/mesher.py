@@ -128,6 +128,11 @@ class Mesher:
     def launches(self) -> int:
         return int(self._lib.vxp_launch_count(self._h))
 
+    def set_overlap(self, enabled: bool):
+        """vxp_ctx_set_overlap: consecutive mesh() calls may overlap on the device; the caller alternates
+        between two output meshes and does not rewrite a call's inputs behind the previous call."""
+        self._check(self._lib.vxp_ctx_set_overlap(self._h, 1 if enabled else 0))
+
     def use_stream(self, stream: Optional["torch.cuda.Stream"]):
         """Run on a torch stream; ``None`` returns to the context's own non-blocking stream."""
         if stream is None:
