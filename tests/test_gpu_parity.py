@@ -99,15 +99,41 @@ def test_golden_cases(G, mesher, mode, mname):
         check_against_oracle(host, vox, nbr, mode, expect_keys=expect)
 
 
+# id palettes: ids that fit the id bit planes of the greedy kernel (1..4), ids that do not (tile equality pass),
+# and ids that differ ONLY above the plane bits (would merge if the planes were used for them)
+PALETTES = {"small": [1, 2, 3, 4], "large": [1000, 1001, 1002, 0xFFFF], "high_bits": [3, 11, 0x103, 0x8003]}
+
+
 @pytest.mark.parametrize("mode,mname", MODES)
+@pytest.mark.parametrize("palette", list(PALETTES))
 @pytest.mark.parametrize("p", [0.01, 0.1, 0.5, 0.9, 0.99])
-def test_differential_random(mesher, mode, mname, p):
+def test_differential_random(mesher, mode, mname, p, palette):
     rng = np.random.default_rng(int(p * 1000) + mode)
-    n = 24
-    vox = np.where(rng.random((n, 32768)) < p, rng.integers(1, 5, (n, 32768)), 0).astype(np.uint16)
+    n = 24 if palette == "small" else 8
+    ids = np.array(PALETTES[palette], dtype=np.uint16)
+    vox = np.where(rng.random((n, 32768)) < p, ids[rng.integers(0, 4, (n, 32768))], 0).astype(np.uint16)
     nbr = rng.integers(-1, n, size=(n, 6)).astype(np.int32)     # arbitrary, asymmetric neighbour links
     host = gpu_mesh(mesher, vox, nbr, mode)
     check_against_oracle(host, vox, nbr, mode)
+
+
+@pytest.mark.parametrize("palette", list(PALETTES))
+def test_layered_ids(mesher, palette):
+    """Terrain-like chunks (solid below a height field, ids in horizontal bands and vertical stripes) for every
+    palette: long greedy runs that must break exactly where the id changes."""
+    rng = np.random.default_rng(3)
+    ids = np.array(PALETTES[palette], dtype=np.uint16)
+    n = 6
+    y = np.arange(32)[None, :, None]
+    v = np.zeros((n, 32, 32, 32), dtype=np.uint16)              # [z][y][x]
+    for i in range(n):
+        h = (8 + 6 * np.sin(np.arange(32)[:, None, None] / 5.0 + i) + 6 * np.cos(np.arange(32)[None, None, :] / 7.0)).astype(int)
+        band = ids[np.clip((h - y) // 2, 0, 3)] if i % 2 == 0 else ids[(np.arange(32)[None, None, :] // (2 + i)) % 4] + 0 * y
+        v[i] = np.where(y <= h, band, 0)
+    vox = v.reshape(n, -1)
+    nbr = rng.integers(-1, n, size=(n, 6)).astype(np.int32)
+    host = gpu_mesh(mesher, vox, nbr, 1)
+    check_against_oracle(host, vox, nbr, 1)
 
 
 def test_many_ids_and_long_runs(mesher):

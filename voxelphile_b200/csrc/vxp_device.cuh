@@ -104,6 +104,25 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     return x;
 }
 
+// N independent transposes, step by step: the N shuffles of a step are in flight together.
+template <int N>
+__device__ __forceinline__ void transpose32xN(uint32_t (&x)[N], int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = (j == 16)  ? 0x0000FFFFu
+                           : (j == 8) ? 0x00FF00FFu
+                           : (j == 4) ? 0x0F0F0F0Fu
+                           : (j == 2) ? 0x33333333u
+                                      : 0x55555555u;
+        const bool up = (lane & j) != 0;
+        uint32_t y[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) y[k] = __shfl_xor_sync(kFull, x[k], j);
+#pragma unroll
+        for (int k = 0; k < N; ++k) x[k] = up ? ((x[k] & ~m) | ((y[k] >> j) & m)) : ((x[k] & m) | ((y[k] << j) & ~m));
+    }
+}
+
 // block-wide helpers (kThreads threads, scratch: kWarps+1 words of shared memory)
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll

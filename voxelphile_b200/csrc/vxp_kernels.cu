@@ -224,12 +224,18 @@ __device__ __forceinline__ void terrain_mesh_chunk(v4::Smem<kGreedy>& sm, short*
     prof.mark(0);
 
     uint32_t v_or = 0, v_and = kFull, o_and = kFull;
-#pragma unroll 1
-    for (int s = 0; s < v4::kSlabs; ++s) v4::convert_slab(sm, s, v_or, v_and, o_and);
-    const v4::ChunkFlags fl = v4::reduce_flags(sm, v_or, v_and, o_and);
+    v4::IdPlanes ip;
+#pragma unroll
+    for (int s = 0; s < v4::kSlabs; ++s) v4::convert_slab(sm, s, v_or, v_and, o_and, ip);
+    const v4::ChunkFlags fl = v4::reduce_flags(sm, v_or, v_and, o_and);   // barrier: the tile has been read
     prof.mark(1);
+    bool with_planes = false;
+    if constexpr (kGreedy) {
+        with_planes = !fl.single_id && fl.small_ids;     // terrain ids are 1..3: always, for a chunk with several ids
+        if (with_planes) v4::store_id_planes(sm.tile.post, ip);
+    }
     const short* hcol = s_h;
-    v4::mesh_tail<kGreedy>(sm, chunk, fl, out, [hcol, Y0](int idx) -> uint32_t {
+    v4::mesh_tail<kGreedy>(sm, chunk, fl, with_planes, out, [hcol, Y0](int idx) -> uint32_t {
         const int x = idx & 31, y = (idx >> 5) & 31, z = idx >> 10;
         return terrain_block(hcol[(z + 1) * 34 + x + 1], Y0 + y);
     }, prof);

@@ -26,6 +26,7 @@
 // Nobody ever waits, so there is no ordering requirement between CTAs, and both paths yield
 // the same bits.
 #pragma once
+#include <type_traits>
 #include "vxp_device.cuh"
 #include "../../include/vxp.h"
 
@@ -171,17 +172,47 @@ __device__ __forceinline__ uint32_t nz8(uint4 q) {
 }
 
 struct ChunkFlags {
-    bool any_solid, all_solid, single_id;
+    bool any_solid, all_solid, single_id, small_ids;
 };
+
+// ---- id bit planes (greedy).  A chunk whose block ids all fit in kIdPlanes bits (small palettes: terrain uses
+// 1..3) gets its three equality volumes from bit planes: bit b of every id is pulled out while the tile is converted
+// (speculatively: whether the ids fit is only known at the end), and the equality rows are then three xors per
+// plane, 32 voxels per instruction (build_masks).  Chunks with larger ids take the per-voxel tile pass
+// (equality_to_regs).  Measured on config 3: the tile pass costs a surface chunk 8.0 k cycles; pulling the planes
+// out of the tile in a pass of their own 4.5 k; during the conversion 1.5 k.
+constexpr int kIdPlanes = 3;
+struct IdPlanes {
+    uint32_t w[kIdPlanes][kSlabs];   // w[b][s]: byte k = bit b of the 8 voxels of this thread's k-th piece of slab s
+};
+// The low kIdPlanes bits of 8 consecutive u16, one plane byte each (bit j of byte b = bit b of element j), placed
+// in byte k of p0 / p1 / p2.  Three steps: the low bytes of the 8 elements are packed into two words (2 PRMT) and
+// folded into one (elements 0..3 in the low nibbles of the bytes, 4..7 in the high nibbles); plane b is then the
+// 8 bits (0x11111111 << b) of that word, and one multiply gathers them into the top byte: bit 8i + 4h + b times
+// 2^(24 - 7i - b) lands on bit 24 + i + 4h, and no two cross terms share a bit position (no carries).
+// 14 instructions, three of them on the FMA pipe, instead of 3 x 13.
+template <int k>
+__device__ __forceinline__ void id_plane_bytes(uint4 q, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+    static_assert(kIdPlanes == 3, "three planes are pulled out here");
+    const uint32_t lo = __byte_perm(q.x, q.y, 0x6420), hi = __byte_perm(q.z, q.w, 0x6420);
+    const uint32_t u = (lo & 0x07070707u) | ((hi & 0x07070707u) << 4);
+    constexpr uint32_t sel = k == 0 ? 0x3217u : k == 1 ? 0x3270u : k == 2 ? 0x3710u : 0x7210u;   // byte k <- top byte of the product
+    p0 = __byte_perm(p0, (u & 0x11111111u) * 0x01020408u, sel);
+    p1 = __byte_perm(p1, (u & 0x22222222u) * 0x00810204u, sel);
+    p2 = __byte_perm(p2, (u & 0x44444444u) * 0x00408102u, sel);
+}
 
 // ------------------------------------------------------------------ tile -> occupancy
 // Convert slab s (layers 8s..8s+7, 16 KiB at `slab`) into sm.occ; accumulates the per-thread flag words.
-template <class SM>
-__device__ __forceinline__ void convert_rows(SM& sm, const uint4* slab, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and) {
+// kPlanes: also pull the id planes out (skipping pieces of air behind a vote was measured no faster).
+template <bool kPlanes, class SM>
+__device__ __forceinline__ void convert_rows(SM& sm, const uint4* slab, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and,
+                                             IdPlanes& ip) {
     const int tid = threadIdx.x;
     unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    uint32_t p0 = 0, p1 = 0, p2 = 0;
+    auto piece = [&](auto kc) {
+        constexpr int k = decltype(kc)::value;
         const int idx = tid + k * kThreads;                 // uint4 index inside the slab: row*4 + piece
         const uint4 q = slab[idx];                          // a warp reads 512 contiguous bytes
         const int row = s * 256 + (idx >> 2), p = idx & 3;  // row = z*32 + y
@@ -190,11 +221,38 @@ __device__ __forceinline__ void convert_rows(SM& sm, const uint4* slab, int s, u
         v_and &= q.x & q.y & q.z & q.w;
         o_and &= bits;
         occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)bits;
+        if constexpr (kPlanes) id_plane_bytes<k>(q, p0, p1, p2);
+    };
+    piece(std::integral_constant<int, 0>{});
+    piece(std::integral_constant<int, 1>{});
+    piece(std::integral_constant<int, 2>{});
+    piece(std::integral_constant<int, 3>{});
+    if constexpr (kPlanes) {
+#pragma unroll
+        for (int t = 0; t < kSlabs; ++t)                    // s is an unrolled loop counter of the caller: ip stays in registers
+            if (t == s) { ip.w[0][t] = p0; ip.w[1][t] = p1; ip.w[2][t] = p2; }
     }
 }
 template <bool kGreedy>
-__device__ __forceinline__ void convert_slab(Smem<kGreedy>& sm, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and) {
-    convert_rows(sm, reinterpret_cast<const uint4*>(sm.tile.vox) + s * (kSlabBytes / 16), s, v_or, v_and, o_and);
+__device__ __forceinline__ void convert_slab(Smem<kGreedy>& sm, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and, IdPlanes& ip) {
+    convert_rows<kGreedy>(sm, reinterpret_cast<const uint4*>(sm.tile.vox) + s * (kSlabBytes / 16), s, v_or, v_and, o_and, ip);
+}
+// Store the id planes into the post area (the tile is dead from here on: the caller has passed the barrier
+// that follows the conversion).  plane b, word (z*kPad + y), bit x.
+__device__ __forceinline__ void store_id_planes(Post<true>& post, const IdPlanes& ip) {
+    const int tid = threadIdx.x;
+    unsigned char* base = reinterpret_cast<unsigned char*>(post.staging);
+#pragma unroll
+    for (int s = 0; s < kSlabs; ++s) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + k * kThreads;
+            const int row = s * 256 + (idx >> 2), p = idx & 3;
+            const int word = (row >> 5) * kPad + (row & 31);
+#pragma unroll
+            for (int b = 0; b < kIdPlanes; ++b) base[(b * kPlaneWords + word) * 4 + p] = (unsigned char)(ip.w[b][s] >> (8 * k));
+        }
+    }
 }
 // Block-wide flags; contains the barrier that publishes the occupancy interior.
 template <class SM>
@@ -212,6 +270,7 @@ __device__ __forceinline__ ChunkFlags reduce_flags(SM& sm, uint32_t v_or, uint32
     f.any_solid = a != 0;
     f.all_solid = (c & 0xFFu) == 0xFFu;
     f.single_id = a == b && (a & 0xFFFFu) == (a >> 16);   // every u16 of the chunk is the same value
+    f.small_ids = ((a | (a >> 16)) & 0xFFFFu) < (1u << kIdPlanes);
     return f;
 }
 
@@ -402,12 +461,17 @@ __device__ __forceinline__ void equality_store(Post<true>& post, const uint32_t 
 
 // ------------------------------------------------------------------ occupancy -> face masks
 // Returns the OR of every mask word this thread produced.
+// with_planes (greedy, ids that fit kIdPlanes bits): the equality rows EX / EY / EZ of each row are derived here
+// from the id bit planes (store_id_planes) instead of having been computed from the tile.
 template <bool kGreedy>
-__device__ __forceinline__ uint32_t build_masks(Smem<kGreedy>& sm, bool with_eq) {
+__device__ __forceinline__ uint32_t build_masks(Smem<kGreedy>& sm, bool with_eq, bool with_planes) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* mask = sm.tile.post.mask;
     uint32_t acc = 0;
-#pragma unroll 4
+    // X planes have u=y, v=z, slice x: their rows are 32x32 bit transposes (lane=y, bit=x) -> (lane=x, bit=y) of what
+    // a warp holds for one z.  The transposes of the warp's four layers run together (independent shuffles).
+    uint32_t tx[8], te[8];          // tx[k] / tx[4+k]: -X / +X visible faces of layer k;  te[k] / te[4+k]: EY / EZ rows
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int z = k * kWarps + warp, y = lane;
         const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
@@ -418,19 +482,56 @@ __device__ __forceinline__ uint32_t build_masks(Smem<kGreedy>& sm, bool with_eq)
         mask[(4 * 32 + z) * kPad + y] = mz;    // -Z : slice z, row y
         mask[(5 * 32 + z) * kPad + y] = pz;    // +Z
         const uint32_t lo = (sm.xh[0][z] >> y) & 1u, hi = (sm.xh[1][z] >> y) & 1u;
-        uint32_t vxm = c & ~((c << 1) | lo);            // -X visible, bit x
-        uint32_t vxq = c & ~((c >> 1) | (hi << 31));    // +X visible, bit x
-        acc |= my | py | mz | pz | vxm | vxq;
-        // transpose (lane=y, bit=x) -> (lane=x, bit=y): X planes have u=y, v=z, slice x
-        const bool anym = __any_sync(kFull, vxm != 0), anyq = __any_sync(kFull, vxq != 0);
-        if (anym) vxm = transpose32(vxm, lane);
-        if (anyq) vxq = transpose32(vxq, lane);
-        mask[(0 * 32 + lane) * kPad + z] = vxm;
-        mask[(1 * 32 + lane) * kPad + z] = vxq;
+        tx[k] = c & ~((c << 1) | lo);                   // -X visible, bit x
+        tx[4 + k] = c & ~((c >> 1) | (hi << 31));       // +X visible, bit x
+        acc |= my | py | mz | pz | tx[k] | tx[4 + k];
+        te[k] = te[4 + k] = 0;
         if constexpr (kGreedy) {
-            if (with_eq && (anym || anyq)) {
-                sm.tile.post.ht[lane * kPad + z] = transpose32(sm.tile.post.ey[z * kPad + y], lane);
-                sm.tile.post.vt[lane * kPad + z] = transpose32(sm.tile.post.ez[z * kPad + y], lane);
+            if (with_eq) {
+                Post<true>& P = sm.tile.post;
+                if (with_planes) {
+                    const uint32_t* B = P.staging + z * kPad + y;
+                    uint32_t dx = 0, dy = 0, dz = 0;
+#pragma unroll
+                    for (int b = 0; b < kIdPlanes; ++b) {
+                        const uint32_t w = B[b * kPlaneWords];
+                        const uint32_t wy = y > 0 ? B[b * kPlaneWords - 1] : w;       // row y = 0 / layer z = 0 are never consulted
+                        const uint32_t wz = z > 0 ? B[b * kPlaneWords - kPad] : w;
+                        dx |= w ^ (w << 1);
+                        dy |= w ^ wy;
+                        dz |= w ^ wz;
+                    }
+                    te[k] = ~dy;
+                    te[4 + k] = ~dz;
+                    P.ex[z * kPad + y] = ~dx;
+                    P.ey[z * kPad + y] = te[k];
+                    P.ez[z * kPad + y] = te[4 + k];
+                } else {
+                    te[k] = P.ey[z * kPad + y];
+                    te[4 + k] = P.ez[z * kPad + y];
+                }
+            }
+        }
+    }
+    uint32_t xany = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xany |= tx[k];
+    const bool anyx = __any_sync(kFull, xany != 0);     // no x face in the warp's four layers: their X mask rows are 0
+    if (anyx) {
+        transpose32xN(tx, lane);
+        if constexpr (kGreedy) {
+            if (with_eq) transpose32xN(te, lane);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int z = k * kWarps + warp;
+        mask[(0 * 32 + lane) * kPad + z] = tx[k];
+        mask[(1 * 32 + lane) * kPad + z] = tx[4 + k];
+        if constexpr (kGreedy) {
+            if (with_eq && anyx) {
+                sm.tile.post.ht[lane * kPad + z] = te[k];
+                sm.tile.post.vt[lane * kPad + z] = te[4 + k];
             }
         }
     }
@@ -947,13 +1048,13 @@ __device__ __forceinline__ void emit_chunk(Smem<kGreedy>& sm, uint32_t chunk, bo
 // ------------------------------------------------------------------ shared tail of both kernels
 // Preconditions: occupancy interior + halo complete and published by a barrier; tile intact.
 template <bool kGreedy, class IdFn>
-__device__ __forceinline__ void mesh_tail(Smem<kGreedy>& sm, uint32_t chunk, ChunkFlags fl, const MeshOut& out, IdFn id_of,
-                                          Prof& prof) {
+__device__ __forceinline__ void mesh_tail(Smem<kGreedy>& sm, uint32_t chunk, ChunkFlags fl, bool with_planes, const MeshOut& out,
+                                          IdFn id_of, Prof& prof) {
     const int tid = threadIdx.x;
     bool with_eq = false;
     if constexpr (kGreedy) {
         with_eq = !fl.single_id;
-        if (with_eq) {
+        if (with_eq && !with_planes) {
             build_active(sm);
             __syncthreads();
             uint32_t res[16];
@@ -965,7 +1066,7 @@ __device__ __forceinline__ void mesh_tail(Smem<kGreedy>& sm, uint32_t chunk, Chu
     if constexpr (kGreedy) {
         __syncthreads();
         prof.mark(3);
-        const bool any = __syncthreads_or(build_masks(sm, with_eq) != 0);
+        const bool any = __syncthreads_or(build_masks(sm, with_eq, with_planes) != 0);
         prof.mark(4);
         if (!any) {
             if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
@@ -1011,11 +1112,12 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
     issue_yz_halo(rows, voxels, nb);
 
     uint32_t v_or = 0, v_and = kFull, o_and = kFull;
-#pragma unroll 1
+    IdPlanes ip;
+#pragma unroll (kGreedy ? kSlabs : 1)
     for (int s = 0; s < kSlabs; ++s) {
         mbar_wait(&sm.mbar[s], parity);
         if (tid == 0 && s + kSlabsInFlight < kSlabs) issue_slab(sm, gvox, s + kSlabsInFlight);
-        convert_slab(sm, s, v_or, v_and, o_and);
+        convert_slab(sm, s, v_or, v_and, o_and, ip);
     }
     prof.mark(0);
     const ChunkFlags fl = reduce_flags(sm, v_or, v_and, o_and);   // barrier: occupancy interior published
@@ -1046,7 +1148,17 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
             return;
         }
     }
-    const bool halo_air = __syncthreads_or(load_halo(sm, voxels, nb, n, bnd, rows, prof));   // barrier: halo published
+    // greedy, several ids that all fit the id planes: the planes replace the tile here (it is dead after the
+    // conversion barrier), stored while the x neighbours' boundary planes are on their way
+    bool with_planes = false;
+    XPoll xp;
+    const bool air_yz = halo_begin(sm, nb, n, bnd, rows, xp);
+    if constexpr (kGreedy) {
+        with_planes = !fl.single_id && fl.small_ids;
+        if (with_planes) store_id_planes(sm.tile.post, ip);
+    }
+    const bool air_x = halo_finish(sm, voxels, nb, n, bnd, xp, prof);
+    const bool halo_air = __syncthreads_or(air_yz || air_x);   // barrier: halo (and id planes) published
     prof.mark(2);
 #if defined(VXP_EXP_STOP) && VXP_EXP_STOP == 2
     if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};   // timing experiment: ... + halo
@@ -1057,7 +1169,7 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
         prof.count(9);
         return;
     }
-    mesh_tail<kGreedy>(sm, chunk, fl, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
+    mesh_tail<kGreedy>(sm, chunk, fl, with_planes, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
 }
 
 // ---- launch chaining.  Consecutive mesh launches of a context may overlap on the device (programmatic
