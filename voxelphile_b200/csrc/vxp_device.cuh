@@ -104,7 +104,9 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     return x;
 }
 
-// N independent transposes, step by step: the N shuffles of a step are in flight together.
+// N independent transposes, step by step: the N shuffles of a step are in flight together.  Per word and step one
+// shuffle, one rotate and one bit select: the lane keeps the half of its bits selected by `keep` and takes the
+// others from its partner's word rotated by j towards them (what a rotate wraps around is masked off).
 template <int N>
 __device__ __forceinline__ void transpose32xN(uint32_t (&x)[N], int lane) {
 #pragma unroll
@@ -115,11 +117,13 @@ __device__ __forceinline__ void transpose32xN(uint32_t (&x)[N], int lane) {
                            : (j == 2) ? 0x33333333u
                                       : 0x55555555u;
         const bool up = (lane & j) != 0;
-        uint32_t y[N];
+        const uint32_t keep = up ? ~m : m;          // up: keep the high halves, take (partner >> j) into the low ones
+        const uint32_t rot = up ? j : 32 - j;       // rotate right by j = shift right; by 32-j = shift left by j
 #pragma unroll
-        for (int k = 0; k < N; ++k) y[k] = __shfl_xor_sync(kFull, x[k], j);
-#pragma unroll
-        for (int k = 0; k < N; ++k) x[k] = up ? ((x[k] & ~m) | ((y[k] >> j) & m)) : ((x[k] & m) | ((y[k] << j) & ~m));
+        for (int k = 0; k < N; ++k) {
+            const uint32_t y = __shfl_xor_sync(kFull, x[k], j);
+            x[k] = (x[k] & keep) | (__funnelshift_r(y, y, rot) & ~keep);
+        }
     }
 }
 

@@ -204,29 +204,35 @@ __device__ __forceinline__ void id_plane_bytes(uint4 q, uint32_t& p0, uint32_t& 
 
 // ------------------------------------------------------------------ tile -> occupancy
 // Convert slab s (layers 8s..8s+7, 16 KiB at `slab`) into sm.occ; accumulates the per-thread flag words.
-// kPlanes: also pull the id planes out (skipping pieces of air behind a vote was measured no faster).
+// kPlanes: also pull the id planes out.
 template <bool kPlanes, class SM>
 __device__ __forceinline__ void convert_rows(SM& sm, const uint4* slab, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and,
                                              IdPlanes& ip) {
     const int tid = threadIdx.x;
     unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
-    uint32_t p0 = 0, p1 = 0, p2 = 0;
-    auto piece = [&](auto kc) {
-        constexpr int k = decltype(kc)::value;
+    uint32_t p0 = 0, p1 = 0, p2 = 0, any = 0;
+    uint4 q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
         const int idx = tid + k * kThreads;                 // uint4 index inside the slab: row*4 + piece
-        const uint4 q = slab[idx];                          // a warp reads 512 contiguous bytes
+        q[k] = slab[idx];                                   // a warp reads 512 contiguous bytes
         const int row = s * 256 + (idx >> 2), p = idx & 3;  // row = z*32 + y
-        const uint32_t bits = nz8(q);
-        v_or |= q.x | q.y | q.z | q.w;
-        v_and &= q.x & q.y & q.z & q.w;
+        const uint32_t bits = nz8(q[k]);
+        v_or |= q[k].x | q[k].y | q[k].z | q[k].w;
+        v_and &= q[k].x & q[k].y & q[k].z & q[k].w;
         o_and &= bits;
+        any |= bits;
         occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)bits;
-        if constexpr (kPlanes) id_plane_bytes<k>(q, p0, p1, p2);
-    };
-    piece(std::integral_constant<int, 0>{});
-    piece(std::integral_constant<int, 1>{});
-    piece(std::integral_constant<int, 2>{});
-    piece(std::integral_constant<int, 3>{});
+    }
+    if constexpr (kPlanes) {
+        // the warp's 4 x 8 rows of this slab: nothing to pull out of 32 rows of air (their planes are 0)
+        if (__any_sync(kFull, any != 0)) {
+            id_plane_bytes<0>(q[0], p0, p1, p2);
+            id_plane_bytes<1>(q[1], p0, p1, p2);
+            id_plane_bytes<2>(q[2], p0, p1, p2);
+            id_plane_bytes<3>(q[3], p0, p1, p2);
+        }
+    }
     if constexpr (kPlanes) {
 #pragma unroll
         for (int t = 0; t < kSlabs; ++t)                    // s is an unrolled loop counter of the caller: ip stays in registers
@@ -254,23 +260,17 @@ __device__ __forceinline__ void store_id_planes(Post<true>& post, const IdPlanes
         }
     }
 }
-// Block-wide flags; contains the barrier that publishes the occupancy interior.
+// Block-wide flags; contains the barrier that publishes the occupancy interior.  Every flag is a predicate each
+// thread can evaluate on its own words, so four barrier reductions do (no shared-memory round).
 template <class SM>
 __device__ __forceinline__ ChunkFlags reduce_flags(SM& sm, uint32_t v_or, uint32_t v_and, uint32_t o_and) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v_or = __reduce_or_sync(kFull, v_or);
-    v_and = __reduce_and_sync(kFull, v_and);
-    o_and = __reduce_and_sync(kFull, o_and);
-    if (lane == 0) { sm.wred[warp][0] = v_or; sm.wred[warp][1] = v_and; sm.wred[warp][2] = o_and; }
-    __syncthreads();
-    uint32_t a = 0, b = kFull, c = kFull;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) { a |= sm.wred[w][0]; b &= sm.wred[w][1]; c &= sm.wred[w][2]; }
+    const uint32_t ref = reinterpret_cast<const uint32_t*>(sm.tile.vox)[0];   // voxels 0 and 1 of the chunk
     ChunkFlags f;
-    f.any_solid = a != 0;
-    f.all_solid = (c & 0xFFu) == 0xFFu;
-    f.single_id = a == b && (a & 0xFFFFu) == (a >> 16);   // every u16 of the chunk is the same value
-    f.small_ids = ((a | (a >> 16)) & 0xFFFFu) < (1u << kIdPlanes);
+    f.any_solid = __syncthreads_or(v_or != 0u);
+    f.all_solid = __syncthreads_and((o_and & 0xFFu) == 0xFFu);
+    // every u16 of the chunk is the same value: every word equals the first one, whose halves are equal
+    f.single_id = __syncthreads_and(v_or == ref && v_and == ref && (ref & 0xFFFFu) == (ref >> 16));
+    f.small_ids = __syncthreads_and(((v_or | (v_or >> 16)) & 0xFFFFu) < (1u << kIdPlanes));
     return f;
 }
 
