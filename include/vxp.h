@@ -49,6 +49,8 @@ typedef enum vxp_pattern { VXP_PATTERN_CHECKER = 0, VXP_PATTERN_SOLID4 = 1 } vxp
 
 typedef struct vxp_coord { int32_t x, y, z; } vxp_coord;           /* chunk coordinate */
 typedef struct vxp_chunk_meta { uint32_t first_quad, quad_count; } vxp_chunk_meta;
+/* One voxel edit: voxel (x,y,z) of stored chunk `chunk` becomes `id` (0 = air).  12 bytes. */
+typedef struct vxp_edit { uint32_t chunk; uint16_t x, y, z, id; } vxp_edit;
 
 /* Batch mesh in DEVICE memory (SPEC §5).  All four arrays are caller-owned.
  * verts must be 32-byte aligned (one quad = one 32-byte store), indices 8-byte aligned. */
@@ -123,6 +125,22 @@ vxp_status vxp_mesh_batch(vxp_ctx *ctx, const uint16_t *d_voxels, const int32_t 
 vxp_status vxp_terrain_mesh_fused(vxp_ctx *ctx, const vxp_coord *d_coords, uint32_t n,
                                   uint64_t seed, vxp_mode mode, const vxp_mesh_dev *out);
 
+/* ---- incremental re-mesh: small batches, latency path -- */
+/* Mesh the `count` chunks named by d_list (indices into d_voxels, each < n; d_nbr6 is the n x 6 table of the
+ * whole batch).  out->meta has `count` entries: entry k belongs to chunk d_list[k]. */
+vxp_status vxp_mesh_list(vxp_ctx *ctx, const uint16_t *d_voxels, const int32_t *d_nbr6, uint32_t n,
+                         const uint32_t *d_list, uint32_t count, vxp_mode mode, const vxp_mesh_dev *out);
+/* Apply m voxel edits to the stored chunks and re-mesh exactly the chunks they invalidate: every edited chunk
+ * and, for an edited voxel on a chunk face, the neighbour across that face (d_nbr6 must be symmetric for the
+ * edited chunks: nbr6[nbr6[c][f]][f^1] == c).  No host round trip: the dirty list and its length stay on the
+ * device.  d_dirty gets the invalidated chunk indices (arbitrary order, no duplicates; room for min(n, 7m)
+ * entries), *d_dirty_count their number; out->meta has min(n, 7m) entries, entry k belongs to chunk d_dirty[k].
+ * Edits of one call must address distinct voxels (of two edits of the same voxel either may win); edits whose
+ * chunk or coordinates are out of range are ignored. */
+vxp_status vxp_remesh_edits(vxp_ctx *ctx, uint16_t *d_voxels, const int32_t *d_nbr6, uint32_t n,
+                            const vxp_edit *d_edits, uint32_t m, vxp_mode mode,
+                            uint32_t *d_dirty, uint32_t *d_dirty_count, const vxp_mesh_dev *out);
+
 /* ---- host level: host pointers in, context-owned pinned results out ---- */
 vxp_status vxp_terrain_fill_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
                                  uint64_t seed, uint16_t *voxels);
@@ -132,6 +150,12 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx *ctx, const uint16_t *voxels, const int3
                                 uint32_t n, uint32_t n_stored, vxp_mode mode, vxp_mesh_host *out);
 vxp_status vxp_terrain_mesh_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
                                  uint64_t seed, vxp_mode mode, vxp_mesh_host *out);
+/* Edit the world that the last vxp_mesh_chunks_host call left resident on the device (its voxels and neighbour
+ * table) and re-mesh what the edits invalidate: 12 bytes per edit go up, only the new meshes come down.
+ * *dirty (context-owned, pinned, *count entries) names the re-meshed chunks; out->meta[k] belongs to (*dirty)[k].
+ * VXP_ERR_BAD_ARG if no world is resident or an edit is out of range. */
+vxp_status vxp_remesh_edits_host(vxp_ctx *ctx, const vxp_edit *edits, uint32_t m, vxp_mode mode,
+                                 vxp_mesh_host *out, const uint32_t **dirty, uint32_t *count);
 
 #ifdef __cplusplus
 }

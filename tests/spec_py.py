@@ -218,3 +218,22 @@ def keys_from_verts(verts: np.ndarray) -> np.ndarray:
     u, v = pos[rows, ua], pos[rows, va]  # vertex 0 is always corner c0
     key = u | v << 6 | along << 12 | f << 18 | wm1 << 21 | hm1 << 26 | b << 31
     return key.astype(np.uint64)
+
+
+# --------------------------------------------------------------------------- SPEC §9 edits
+def apply_edits(vox: np.ndarray, nbr, edits, n_mesh=None) -> list[int]:
+    """Apply edits (iterable of (chunk, x, y, z, id)) to vox [n_stored, 32768] in place; return the sorted
+    list of invalidated chunks (SPEC §9)."""
+    n = vox.shape[0] if n_mesh is None else n_mesh
+    dirty = set()
+    for c, x, y, z, b in edits:
+        vox[c, x + 32 * y + 1024 * z] = b
+        dirty.add(int(c))
+        if nbr is None:
+            continue
+        for coord, lo_f in ((x, 0), (y, 2), (z, 4)):
+            for f in ((lo_f,) if coord == 0 else (lo_f + 1,) if coord == 31 else ()):
+                nb = int(nbr[c][f])
+                if 0 <= nb < n:
+                    dirty.add(nb)
+    return sorted(dirty)

@@ -9,6 +9,7 @@ import pytest
 
 import oracle_lib as O
 import spec_py as S
+from voxelphile_b200 import EDIT_DTYPE
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "spec_v1.npz")
@@ -443,5 +444,109 @@ def test_overlapped_launches(mode, mname):
         h2 = o2.to_host()
         assert h2.total_quads == serial[0][0] and np.array_equal(_chunk_hashes(h2), serial[0][2])
         m.set_overlap(False)
+    finally:
+        m.close()
+
+
+# --------------------------------------------------------------------------- SPEC §9: incremental re-mesh
+def _edit_world():
+    from voxelphile_b200 import grid_coords, neighbour_table
+    coords = grid_coords((0, 6, 0), (4, 10, 4))               # 64 chunks around the terrain surface
+    return coords, neighbour_table(coords), O.terrain_fill_batch(42, coords)
+
+
+def _random_edits(rng, n, m):
+    """m edits of distinct voxels; a third of them pinned to chunk faces / edges / corners."""
+    from voxelphile_b200 import EDIT_DTYPE
+    seen, rows = set(), []
+    while len(rows) < m:
+        c = int(rng.integers(0, n))
+        xyz = [int(v) for v in rng.integers(0, 32, 3)]
+        if rng.random() < 0.35:
+            for a in rng.choice(3, size=int(rng.integers(1, 4)), replace=False):
+                xyz[a] = int(rng.choice([0, 31]))
+        if (c, *xyz) in seen:
+            continue
+        seen.add((c, *xyz))
+        rows.append((c, *xyz, int(rng.choice([0, 0, 1, 2, 3, 9, 0x7FFF]))))
+    return np.array(rows, dtype=EDIT_DTYPE), rows
+
+
+def _check_remeshed(host, dirty, vox, nbr, mode):
+    for k, c in enumerate(dirty):
+        nbs = [None if nbr[c, f] < 0 else vox[nbr[c, f]] for f in range(6)]
+        want = O.mesh_chunk_keys(vox[c], nbs, mode)
+        assert int(host.meta[k, 1]) == len(want), (k, c)
+        got = np.sort(S.keys_from_verts(host.chunk(k)[0])) if len(want) else np.zeros(0, np.uint64)
+        assert np.array_equal(got, want), (k, c)
+    assert host.total_quads == int(host.meta[:len(dirty), 1].sum())
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+@pytest.mark.parametrize("m", [1, 40, 500])
+def test_remesh_edits_device(mesher, mode, mname, m):
+    import torch
+    coords, nbr, vox = _edit_world()
+    rng = np.random.default_rng(100 + m + mode)
+    edits, rows = _random_edits(rng, len(coords), m)
+    dvox, dn = dev(vox.view(np.int16)), dev(nbr)
+    dirty_t, count_t, out = mesher.remesh_edits(dvox, dn, dev(edits.view(np.int32).reshape(-1, 3)), mode)
+    torch.cuda.synchronize()
+    want_dirty = S.apply_edits(vox, nbr, rows)
+    cnt = int(count_t.item())
+    dirty = dirty_t[:cnt].cpu().numpy().astype(np.int64)
+    assert sorted(dirty.tolist()) == want_dirty and len(set(dirty.tolist())) == cnt
+    assert np.array_equal(dvox.cpu().numpy().view(np.uint16), vox), "voxels after the edits"
+    _check_remeshed(out.to_host(), dirty, vox, nbr, mode)
+
+
+def test_mesh_list(mesher):
+    """An explicit list: arbitrary order, duplicates allowed, meta entry k belongs to list[k]."""
+    import torch
+    coords, nbr, vox = _edit_world()
+    lst = np.array([5, 63, 5, 0, 21, 22, 37], dtype=np.int32)
+    for mode, _ in MODES:
+        out = mesher.mesh_list(dev(vox.view(np.int16)), dev(nbr), dev(lst), mode)
+        torch.cuda.synchronize()
+        _check_remeshed(out.to_host(), lst, vox, nbr, mode)
+    empty = mesher.mesh_list(dev(vox.view(np.int16)), dev(nbr), dev(np.zeros(0, np.int32)), 1)
+    torch.cuda.synchronize()
+    assert int(empty.total.item()) == 0
+
+
+def test_remesh_edits_host(mesher):
+    """Host-level flow: upload and mesh a world once, then send edits (12 bytes each) and get back only the
+    re-meshed chunks; several rounds of edits accumulate in the resident world."""
+    from voxelphile_b200 import EDIT_DTYPE, MeshError
+    coords, nbr, vox = _edit_world()
+    rng = np.random.default_rng(7)
+    full = mesher.mesh_host(vox, nbr, 1)
+    for rnd, m in enumerate((3, 60, 1)):
+        edits, rows = _random_edits(rng, len(coords), m)
+        dirty, host = mesher.remesh_edits_host(edits, rnd % 2)
+        want_dirty = S.apply_edits(vox, nbr, rows)
+        assert sorted(dirty.tolist()) == want_dirty
+        _check_remeshed(host, dirty.astype(np.int64), vox, nbr, rnd % 2)
+    # the resident world now equals the edited host copy: a full re-mesh of it agrees with the oracle
+    again = mesher.mesh_host(vox, nbr, 1)
+    want_hash, want_cnt = O.mesh_batch_hash(vox, nbr, 1)
+    assert np.array_equal(again.meta[:, 1], want_cnt) and np.array_equal(_chunk_hashes(again), want_hash)
+    assert full.total_quads != again.total_quads or not np.array_equal(full.meta, again.meta)
+    dirty, host = mesher.remesh_edits_host(np.zeros(0, EDIT_DTYPE), 1)
+    assert len(dirty) == 0 and host.total_quads == 0
+    with pytest.raises(MeshError) as e:
+        mesher.remesh_edits_host(np.array([(64, 0, 0, 0, 1)], dtype=EDIT_DTYPE), 1)
+    assert e.value.kind == "BadArg"
+    with pytest.raises(MeshError):
+        mesher.remesh_edits_host(np.array([(0, 32, 0, 0, 1)], dtype=EDIT_DTYPE), 1)
+
+
+def test_remesh_needs_a_resident_world():
+    from voxelphile_b200 import EDIT_DTYPE, Mesher, MeshError
+    m = Mesher(0)
+    try:
+        with pytest.raises(MeshError) as e:
+            m.remesh_edits_host(np.array([(0, 1, 1, 1, 1)], dtype=EDIT_DTYPE), 1)
+        assert e.value.kind == "BadArg"
     finally:
         m.close()

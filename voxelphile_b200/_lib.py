@@ -55,6 +55,12 @@ SIGNATURES = {
     "vxp_pattern_fill_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]),
     "vxp_mesh_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(MeshDev)]),
     "vxp_terrain_mesh_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(MeshDev)]),
+    "vxp_mesh_list": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
+                      C.POINTER(MeshDev)]),
+    "vxp_remesh_edits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
+                         C.c_void_p, C.c_void_p, C.POINTER(MeshDev)]),
+    "vxp_remesh_edits_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(MeshHost),
+                              C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "vxp_terrain_fill_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]),
     "vxp_mesh_chunks_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                              C.POINTER(MeshHost)]),

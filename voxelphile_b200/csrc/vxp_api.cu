@@ -36,6 +36,14 @@ struct vxp_ctx {
     bool launched = false;                      // a mesh launch has been enqueued ...
     cudaStream_t launch_stream = nullptr;       // ... on this stream
     bool chain_open = false;                    // ... with overlap enabled, and nothing else of ours since
+    // incremental re-mesh: per-chunk "on the dirty list" stamps, and the host-level call's resident world / arenas
+    uint32_t* d_dirty_flags = nullptr;  size_t dirty_cap = 0;  uint32_t dirty_epoch = 0;
+    uint32_t world_n = 0, world_stored = 0;  bool world_has_nbr = false, world_valid = false;
+    vxp_edit* d_edits = nullptr;        size_t edits_cap = 0;
+    uint32_t* d_dirty = nullptr;        size_t dirty_list_cap = 0;
+    uint32_t* d_dirty_count = nullptr;
+    uint32_t* h_dirty = nullptr;        size_t h_dirty_cap = 0;
+    uint32_t* h_dirty_count = nullptr;
     cudaEvent_t ev_chain = nullptr;
     // column scratch of the fused terrain+mesh path (vxp_launch.h: ColumnScratch)
     unsigned char* d_columns = nullptr;  size_t columns_cap = 0;   // chunks
@@ -303,6 +311,8 @@ vxp_status vxp_ctx_create(int device, vxp_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_dirty_count), sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_dirty_count), sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_total), sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_totals), vxp_ctx::kMaxSlices * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
@@ -339,6 +349,12 @@ void vxp_ctx_destroy(vxp_ctx* ctx) {
         cudaFree(ctx->d_planes[k]);
     }
     cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_dirty_flags);
+    cudaFree(ctx->d_edits);
+    cudaFree(ctx->d_dirty);
+    cudaFree(ctx->d_dirty_count);
+    cudaFreeHost(ctx->h_dirty);
+    cudaFreeHost(ctx->h_dirty_count);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     cudaFreeHost(ctx->h_meta);
     cudaFreeHost(ctx->h_verts);
@@ -475,6 +491,81 @@ vxp_status vxp_terrain_mesh_fused(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
     return VXP_OK;
 }
 
+// ------------------------------------------------------------------ incremental re-mesh
+
+namespace {
+// "on the dirty list" stamps for n chunks: zeroed on allocation and when the epoch wraps
+vxp_status next_dirty_flags(vxp_ctx* ctx, uint32_t n, uint32_t* epoch) {
+    if (n > ctx->dirty_cap) {
+        const size_t want = (size_t)n + n / 4;
+        if (ctx->d_dirty_flags) VXP_CUDA(ctx, cudaFree(ctx->d_dirty_flags));
+        ctx->d_dirty_flags = nullptr;
+        ctx->dirty_cap = 0;
+        VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_dirty_flags), want * sizeof(uint32_t)));
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_dirty_flags, 0, want * sizeof(uint32_t), ctx->stream));
+        ctx->dirty_cap = want;
+        ctx->dirty_epoch = 0;
+    }
+    if (++ctx->dirty_epoch == 0xFFFFFFFFu) {
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_dirty_flags, 0, ctx->dirty_cap * sizeof(uint32_t), ctx->stream));
+        ctx->dirty_epoch = 1;
+    }
+    *epoch = ctx->dirty_epoch;
+    return VXP_OK;
+}
+uint32_t max_dirty(uint32_t n, uint32_t m) { return (uint64_t)m * 7 < n ? m * 7 : n; }
+
+// serialise against whatever mesh launch of this context may still be running on another stream
+vxp_status join_chain(vxp_ctx* ctx) {
+    if (ctx->launched && ctx->launch_stream != ctx->stream) {
+        VXP_CUDA(ctx, cudaEventRecord(ctx->ev_chain, ctx->launch_stream));
+        VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0));
+    }
+    ctx->launched = true;
+    ctx->launch_stream = ctx->stream;
+    ctx->chain_open = false;
+    return VXP_OK;
+}
+}  // namespace
+
+vxp_status vxp_mesh_list(vxp_ctx* ctx, const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n,
+                         const uint32_t* d_list, uint32_t count, vxp_mode mode, const vxp_mesh_dev* out) {
+    if (!ctx || !valid_mode(mode) || !valid_out(out, count)) return VXP_ERR_BAD_ARG;
+    if (count && (!d_voxels || !aligned16(d_voxels) || !d_list || n == 0)) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    vxp_status s;
+    if ((s = join_chain(ctx)) != VXP_OK) return s;
+    VXP_CUDA(ctx, vxp::launch_mesh_list(d_voxels, d_nbr6, n, d_list, nullptr, count, mode == VXP_MODE_GREEDY, *out,
+                                        ctx->d_counters + ctx->slot, ctx->stream));
+    if (count) {
+        ctx->launches += 1;
+        ctx->slot ^= 1;
+    }
+    return VXP_OK;
+}
+
+vxp_status vxp_remesh_edits(vxp_ctx* ctx, uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, const vxp_edit* d_edits,
+                            uint32_t m, vxp_mode mode, uint32_t* d_dirty, uint32_t* d_dirty_count, const vxp_mesh_dev* out) {
+    if (!ctx || !valid_mode(mode) || !d_dirty_count) return VXP_ERR_BAD_ARG;
+    const uint32_t cap = max_dirty(n, m);
+    if (!valid_out(out, cap)) return VXP_ERR_BAD_ARG;
+    if (m && (!d_voxels || !aligned16(d_voxels) || !d_edits || !d_dirty || n == 0)) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    vxp_status s;
+    if ((s = join_chain(ctx)) != VXP_OK) return s;
+    uint32_t epoch = 0;
+    if (m && (s = next_dirty_flags(ctx, n, &epoch)) != VXP_OK) return s;
+    VXP_CUDA(ctx, vxp::launch_apply_edits(d_voxels, d_nbr6, n, d_edits, m, ctx->d_dirty_flags, epoch, d_dirty, d_dirty_count,
+                                          ctx->stream));
+    VXP_CUDA(ctx, vxp::launch_mesh_list(d_voxels, d_nbr6, n, d_dirty, d_dirty_count, m ? cap : 0, mode == VXP_MODE_GREEDY, *out,
+                                        ctx->d_counters + ctx->slot, ctx->stream));
+    if (m) {
+        ctx->launches += 2;
+        ctx->slot ^= 1;
+    }
+    return VXP_OK;
+}
+
 // ------------------------------------------------------------------ host level
 
 vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t n, uint64_t seed,
@@ -484,6 +575,7 @@ vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
     DeviceGuard g(ctx->device);
     vxp_status s;
     if ((s = grow_device(ctx, &ctx->d_coords, &ctx->coords_cap, n, 1)) != VXP_OK) return s;
+    ctx->world_valid = false;            // the voxel arena is re-used
     if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
     ctx->chain_open = false;
     VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_coords, coords, (size_t)n * sizeof(vxp_coord), cudaMemcpyHostToDevice,
@@ -517,6 +609,10 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
     if ((s = grow_host_quads(ctx, ctx->quads_cap)) != VXP_OK) return s;
     const int32_t* d_nbr = nbr6 ? ctx->d_nbr6 : nullptr;
     const int greedy = mode == VXP_MODE_GREEDY;
+    ctx->world_n = n;                    // the world stays resident for vxp_remesh_edits_host
+    ctx->world_stored = n_stored;
+    ctx->world_has_nbr = nbr6 != nullptr;
+    ctx->world_valid = n > 0;
     const size_t chunk_bytes = (size_t)VXP_CHUNK_VOXELS * sizeof(uint16_t);
     uint64_t total = 0;
     bool done = false;
@@ -628,6 +724,69 @@ vxp_status vxp_terrain_mesh_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
             return vxp::launch_terrain_mesh(ctx->d_coords, n, seed, mode == VXP_MODE_GREEDY, dev, cols, ctx->stream);
         },
         out);
+}
+
+// Edits go up (12 bytes each), the voxels are patched and the dirty chunks re-meshed on the device, and only the
+// dirty list and the new meshes come down.  Two synchronisations: one to learn how many quads to fetch, one at the end.
+vxp_status vxp_remesh_edits_host(vxp_ctx* ctx, const vxp_edit* edits, uint32_t m, vxp_mode mode, vxp_mesh_host* out,
+                                 const uint32_t** dirty, uint32_t* count) {
+    if (!ctx || !out || !dirty || !count || !valid_mode(mode) || (m && !edits)) return VXP_ERR_BAD_ARG;
+    if (!ctx->world_valid) return VXP_ERR_BAD_ARG;
+    const uint32_t n = ctx->world_n;
+    for (uint32_t i = 0; i < m; ++i)
+        if (edits[i].chunk >= n || edits[i].x >= 32 || edits[i].y >= 32 || edits[i].z >= 32) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    vxp_status s;
+    const uint32_t cap = max_dirty(n, m);
+    if ((s = grow_device(ctx, &ctx->d_edits, &ctx->edits_cap, m, 1)) != VXP_OK) return s;
+    if ((s = grow_device(ctx, &ctx->d_dirty, &ctx->dirty_list_cap, cap, 1)) != VXP_OK) return s;
+    if ((s = grow_pinned(ctx, &ctx->h_dirty, &ctx->h_dirty_cap, cap, 1)) != VXP_OK) return s;
+    if ((s = grow_pinned(ctx, &ctx->h_meta, &ctx->h_meta_cap, cap, 1)) != VXP_OK) return s;
+    if ((s = grow_device(ctx, &ctx->d_meta, &ctx->meta_cap, cap, 1)) != VXP_OK) return s;
+    if ((s = grow_quads(ctx, (size_t)cap * 1024 + 4096)) != VXP_OK) return s;
+    uint64_t total = 0;
+    uint32_t cnt = 0;
+    if (m) VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_edits, edits, (size_t)m * sizeof(vxp_edit), cudaMemcpyHostToDevice, ctx->stream));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const vxp_mesh_dev dev{ctx->d_verts, ctx->d_indices, ctx->d_meta, ctx->d_total, ctx->quads_cap};
+        if (attempt == 0) {
+            s = vxp_remesh_edits(ctx, ctx->d_voxels, ctx->world_has_nbr ? ctx->d_nbr6 : nullptr, n, ctx->d_edits, m, mode,
+                                 ctx->d_dirty, ctx->d_dirty_count, &dev);
+        } else {   // the arena was too small: the voxels are already patched and the list is on the device
+            VXP_CUDA(ctx, vxp::launch_mesh_list(ctx->d_voxels, ctx->world_has_nbr ? ctx->d_nbr6 : nullptr, n, ctx->d_dirty,
+                                                ctx->d_dirty_count, cap, mode == VXP_MODE_GREEDY, dev,
+                                                ctx->d_counters + ctx->slot, ctx->stream));
+            ctx->launches += 1;
+            ctx->slot ^= 1;
+            s = VXP_OK;
+        }
+        if (s != VXP_OK) return s;
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_total, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_dirty_count, ctx->d_dirty_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (cap) {
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_dirty, ctx->d_dirty, (size_t)cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_meta, ctx->d_meta, (size_t)cap * sizeof(vxp_chunk_meta), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        total = m ? *ctx->h_total : 0;
+        cnt = m ? *ctx->h_dirty_count : 0;
+        if (total <= ctx->quads_cap) break;
+        if (attempt == 1) return VXP_ERR_CAPACITY;
+        if ((s = grow_quads(ctx, total)) != VXP_OK) return s;
+    }
+    if ((s = grow_host_quads(ctx, total)) != VXP_OK) return s;
+    if (total) {
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_verts, ctx->d_verts, total * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices, ctx->d_indices, total * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    out->verts = ctx->h_verts;
+    out->indices = ctx->h_indices;
+    out->meta = ctx->h_meta;
+    out->total_quads = total;
+    *dirty = ctx->h_dirty;
+    *count = cnt;
+    return VXP_OK;
 }
 
 }  // extern "C"

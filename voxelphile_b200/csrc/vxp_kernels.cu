@@ -317,7 +317,7 @@ cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, u
     if (lo >= hi) return cudaSuccess;
     const v4::Bnd bnd{scratch.tags, scratch.planes, scratch.epoch};
     const uint32_t grid = hi - lo;
-    const v4::Chain chain{nullptr};
+    const v4::Chain chain{nullptr, nullptr, nullptr};
     return greedy ? launch_mesh_kernel<true>(grid, 0, stream, d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd, chain)
                   : launch_mesh_kernel<false>(grid, 0, stream, d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd, chain);
 }
@@ -331,9 +331,63 @@ cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_
     v4::MeshOut out = mesh_out(o);
     out.total = counter;
     out.cta_inc = v4::kCtaOne;
-    const v4::Chain chain{reinterpret_cast<unsigned long long*>(o.total_quads)};
+    const v4::Chain chain{reinterpret_cast<unsigned long long*>(o.total_quads), nullptr, nullptr};
     return greedy ? launch_mesh_kernel<true>(n, overlap, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain)
                   : launch_mesh_kernel<false>(n, overlap, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain);
+}
+
+// ---- incremental re-mesh
+// One thread per edit: write the voxel, mark the chunk and - for a voxel on a chunk face - the neighbour across
+// that face (a symmetric neighbour table is assumed: the chunk that sees this voxel through its halo is nbr6[c][f]).
+// flags[c] == epoch means "already on the list"; the thread that flips it appends the chunk.
+__global__ void __launch_bounds__(kThreads) apply_edits_kernel(uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6,
+                                                                uint32_t n, const vxp_edit* __restrict__ edits, uint32_t m,
+                                                                uint32_t* __restrict__ flags, uint32_t epoch,
+                                                                uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= m) return;
+    const vxp_edit e = edits[i];
+    if (e.chunk >= n || e.x >= 32u || e.y >= 32u || e.z >= 32u) return;     // out of range: ignored
+    voxels[(size_t)e.chunk * VXP_CHUNK_VOXELS + e.x + 32u * e.y + 1024u * e.z] = e.id;
+    auto mark = [&](uint32_t c) {
+        if (atomicExch(flags + c, epoch) != epoch) list[atomicAdd(count, 1u)] = c;
+    };
+    mark(e.chunk);
+    if (nbr6 == nullptr) return;
+    const int32_t* nb = nbr6 + 6 * (size_t)e.chunk;
+    auto across = [&](int f) {
+        const int32_t c = __ldg(nb + f);
+        if (c >= 0 && (uint32_t)c < n) mark((uint32_t)c);
+    };
+    if (e.x == 0u) across(0);
+    if (e.x == 31u) across(1);
+    if (e.y == 0u) across(2);
+    if (e.y == 31u) across(3);
+    if (e.z == 0u) across(4);
+    if (e.z == 31u) across(5);
+}
+
+cudaError_t launch_apply_edits(uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, const vxp_edit* d_edits, uint32_t m,
+                               uint32_t* d_flags, uint32_t epoch, uint32_t* d_list, uint32_t* d_count, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(d_count, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess || m == 0) return e;
+    apply_edits_kernel<<<(m + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_voxels, d_nbr6, n, d_edits, m, d_flags, epoch,
+                                                                              d_list, d_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh_list(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, const uint32_t* d_list,
+                             const uint32_t* d_count, uint32_t max_count, int greedy, const vxp_mesh_dev& o,
+                             unsigned long long* counter, cudaStream_t stream) {
+    if (max_count == 0) return cudaMemsetAsync(o.total_quads, 0, sizeof(uint64_t), stream);
+    if (max_count > (1u << 22) - 1u) return cudaErrorInvalidValue;
+    const v4::Bnd bnd{nullptr, nullptr, 0};      // the x neighbours are not meshed alongside: their boundary is gathered
+    v4::MeshOut out = mesh_out(o);
+    out.total = counter;
+    out.cta_inc = v4::kCtaOne;
+    const v4::Chain chain{reinterpret_cast<unsigned long long*>(o.total_quads), d_list, d_count};
+    return greedy ? launch_mesh_kernel<true>(max_count, 0, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain)
+                  : launch_mesh_kernel<false>(max_count, 0, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain);
 }
 
 size_t boundary_tag_bytes(uint32_t n) { return (size_t)n * sizeof(uint32_t); }

@@ -51,6 +51,15 @@ cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_
 // chunks [lo, hi) of a batch of n; does NOT zero *out.total_quads (ranges of one batch accumulate into it)
 cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi,
                               int greedy, const vxp_mesh_dev& out, const BoundaryScratch& scratch, cudaStream_t stream);
+// Incremental re-mesh.  launch_apply_edits writes the voxels and builds the list of chunks whose
+// mesh they invalidate (d_flags: n words, context-owned, zeroed on allocation; epoch distinguishes calls; d_count
+// is zeroed here).  launch_mesh_list meshes chunk d_list[b] into meta entry b for b < *d_count <= max_count
+// (max_count CTAs are launched; the count stays on the device; d_count == nullptr: the count is max_count).
+cudaError_t launch_apply_edits(uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, const vxp_edit* d_edits, uint32_t m,
+                               uint32_t* d_flags, uint32_t epoch, uint32_t* d_list, uint32_t* d_count, cudaStream_t stream);
+cudaError_t launch_mesh_list(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, const uint32_t* d_list,
+                             const uint32_t* d_count, uint32_t max_count, int greedy, const vxp_mesh_dev& out,
+                             unsigned long long* counter, cudaStream_t stream);
 cudaError_t launch_terrain_mesh(const vxp_coord* d_coords, uint32_t n, uint64_t seed, int greedy,
                                 const vxp_mesh_dev& out, const ColumnScratch& columns, cudaStream_t stream);
 }  // namespace vxp

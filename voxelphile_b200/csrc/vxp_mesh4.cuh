@@ -1092,12 +1092,12 @@ __device__ __forceinline__ void issue_slab(Smem<kGreedy>& sm, const uint16_t* gv
                 reinterpret_cast<const unsigned char*>(gvox) + s * kSlabBytes, kSlabBytes, &sm.mbar[s]);
 }
 
-// One chunk, start to finish.  The four tile barriers have been initialised by the caller and complete once
+// One chunk, start to finish; its meta entry is out.meta[mi].  The four tile barriers have been initialised by the caller and complete once
 // per chunk: `parity` is the phase to wait for (0 for the first chunk of a CTA, then alternating).
 // Every return is block-uniform.
 template <bool kGreedy>
 __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6,
-                                           uint32_t n, uint32_t chunk, uint32_t parity, const MeshOut& out, const Bnd& bnd) {
+                                           uint32_t n, uint32_t chunk, uint32_t mi, uint32_t parity, const MeshOut& out, const Bnd& bnd) {
     const int tid = threadIdx.x;
     const uint16_t* gvox = voxels + (size_t)chunk * VXP_CHUNK_VOXELS;
     Prof prof;
@@ -1123,12 +1123,12 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
     const ChunkFlags fl = reduce_flags(sm, v_or, v_and, o_and);   // barrier: occupancy interior published
     prof.mark(1);
 #if defined(VXP_EXP_STOP) && VXP_EXP_STOP == 1
-    if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};   // timing experiment: stream + convert only
+    if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};   // timing experiment: stream + convert only
     return;
 #endif
     if (bnd.tags) publish_boundary(sm, bnd, chunk, fl);
     if (!fl.any_solid) {                        // all air: no faces
-        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+        if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};
         prof.count(8);
         return;
     }
@@ -1144,7 +1144,7 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
             __syncthreads();                    // x halo published
             prof.mark(2);
             packed += culled_count<true>(sm);
-            culled_emit(sm, chunk, packed, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
+            culled_emit(sm, mi, packed, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
             return;
         }
     }
@@ -1161,15 +1161,15 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
     const bool halo_air = __syncthreads_or(air_yz || air_x);   // barrier: halo (and id planes) published
     prof.mark(2);
 #if defined(VXP_EXP_STOP) && VXP_EXP_STOP == 2
-    if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};   // timing experiment: ... + halo
+    if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};   // timing experiment: ... + halo
     return;
 #endif
     if (fl.all_solid && !halo_air) {            // buried: no faces
-        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+        if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};
         prof.count(9);
         return;
     }
-    mesh_tail<kGreedy>(sm, chunk, fl, with_planes, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
+    mesh_tail<kGreedy>(sm, mi, fl, with_planes, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
 }
 
 // ---- launch chaining.  Consecutive mesh launches of a context may overlap on the device (programmatic
@@ -1184,6 +1184,10 @@ __device__ __forceinline__ void mesh_chunk(Smem<kGreedy>& sm, const uint16_t* __
 // Without the launch attribute (the default) both instructions are no-ops and launches serialise as usual.
 struct Chain {
     unsigned long long* user_total;   // the caller's total_quads; nullptr: no check-in, no hand-over (MeshOut::cta_inc == 0)
+    // list mode (incremental re-mesh): CTA b meshes chunk list[b] into meta entry b, for b < *list_count; the
+    // grid is an upper bound of the count, which only the device knows.  nullptr: CTA b meshes chunk chunk0 + b.
+    const uint32_t* list;
+    const uint32_t* list_count;       // nullptr: the whole grid is the list
 };
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -1200,7 +1204,14 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
             MeshOut out, Bnd bnd, Chain chain) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<kGreedy>& sm = *reinterpret_cast<Smem<kGreedy>*>(smem_raw);
-    const uint32_t chunk = chunk0 + blockIdx.x;
+    uint32_t chunk = chunk0 + blockIdx.x, mi = chunk;
+    bool active = chunk < hi;
+    if (chain.list != nullptr) {
+        active = chain.list_count == nullptr || blockIdx.x < __ldg(chain.list_count);
+        chunk = active ? __ldg(chain.list + blockIdx.x) : 0u;
+        mi = blockIdx.x;
+        active = active && chunk < n;
+    }
     const bool closer = chain.user_total != nullptr && blockIdx.x == gridDim.x - 1;
     if (threadIdx.x == 0) {
         if (closer) griddep_wait();             // the previous launch has completed (its slot is free for the next one)
@@ -1215,7 +1226,7 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
 #ifdef VXP_PROFILE
     if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][0] = prof_now();
 #endif
-    if (chunk < hi) mesh_chunk(sm, voxels, nbr6, n, chunk, 0u, out, bnd);
+    if (active) mesh_chunk(sm, voxels, nbr6, n, chunk, mi, 0u, out, bnd);
 #ifdef VXP_PROFILE
     if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][1] = prof_now();
 #endif

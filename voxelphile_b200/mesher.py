@@ -23,6 +23,8 @@ from . import _lib
 CULLED, GREEDY = _lib.MODE_CULLED, _lib.MODE_GREEDY
 CHUNK_DIM = 32
 CHUNK_VOXELS = _lib.CHUNK_VOXELS
+# vxp_edit (include/vxp.h): voxel (x,y,z) of stored chunk `chunk` becomes `id`
+EDIT_DTYPE = np.dtype([("chunk", np.uint32), ("x", np.uint16), ("y", np.uint16), ("z", np.uint16), ("id", np.uint16)])
 
 _KINDS = {
     _lib.VXP_ERR_BAD_ARG: "BadArg",
@@ -213,6 +215,53 @@ class Mesher:
         self._check(self._lib.vxp_terrain_mesh_fused(self._h, coords.data_ptr(), n, seed & (2**64 - 1), mode,
                                                      C.byref(s)))
         return out
+
+    # ------------------------------------------------------------ incremental re-mesh
+    def mesh_list(self, voxels: "torch.Tensor", nbr6: Optional["torch.Tensor"], chunk_list: "torch.Tensor", mode: int,
+                  out: Optional[DeviceMesh] = None, capacity: Optional[int] = None) -> DeviceMesh:
+        """vxp_mesh_list: mesh the chunks named by ``chunk_list`` (int32/uint32 device tensor); meta entry k
+        belongs to chunk chunk_list[k]."""
+        n, count = voxels.shape[0], int(chunk_list.shape[0])
+        assert chunk_list.is_cuda and chunk_list.is_contiguous() and chunk_list.element_size() == 4
+        if out is None:
+            out = self.alloc_mesh(count, capacity if capacity is not None else count * 4096)
+        s = self._mesh_struct(out)
+        self._check(self._lib.vxp_mesh_list(self._h, voxels.data_ptr(), nbr6.data_ptr() if nbr6 is not None else None,
+                                            n, chunk_list.data_ptr(), count, mode, C.byref(s)))
+        return out
+
+    def remesh_edits(self, voxels: "torch.Tensor", nbr6: Optional["torch.Tensor"], edits: "torch.Tensor", mode: int,
+                     capacity: Optional[int] = None):
+        """vxp_remesh_edits: apply ``edits`` (device tensor of EDIT_DTYPE records viewed as int32 [m,3]) to
+        ``voxels`` in place and re-mesh the invalidated chunks.  Returns (dirty list tensor, count tensor, DeviceMesh);
+        nothing is synchronised."""
+        import torch
+        n, m = voxels.shape[0], int(edits.shape[0])
+        cap = min(n, 7 * m)
+        dirty = torch.empty(max(cap, 1), dtype=torch.int32, device=voxels.device)
+        count = torch.zeros(1, dtype=torch.int32, device=voxels.device)
+        out = self.alloc_mesh(cap, capacity if capacity is not None else cap * 4096)
+        s = self._mesh_struct(out)
+        self._check(self._lib.vxp_remesh_edits(self._h, voxels.data_ptr(), nbr6.data_ptr() if nbr6 is not None else None,
+                                               n, edits.data_ptr(), m, mode, dirty.data_ptr(), count.data_ptr(), C.byref(s)))
+        return dirty, count, out
+
+    def remesh_edits_host(self, edits: np.ndarray, mode: int, copy: bool = True):
+        """vxp_remesh_edits_host: edit the world left resident by the last mesh_host call.  Returns
+        (dirty chunk indices, HostMesh whose meta[k] belongs to dirty[k])."""
+        edits = np.ascontiguousarray(edits, dtype=EDIT_DTYPE)
+        h = _lib.MeshHost()
+        dptr, cnt = C.c_void_p(), C.c_uint32()
+        self._check(self._lib.vxp_remesh_edits_host(self._h, edits.ctypes.data, edits.shape[0], mode, C.byref(h),
+                                                    C.byref(dptr), C.byref(cnt)))
+        k = int(cnt.value)
+        if k:
+            buf = (C.c_char * (4 * k)).from_address(dptr.value)
+            dirty = np.frombuffer(buf, dtype=np.uint32, count=k)
+            dirty = dirty.copy() if copy else dirty
+        else:
+            dirty = np.empty(0, np.uint32)
+        return dirty, self._host_result(h, k, copy)
 
     # ------------------------------------------------------------ host level (numpy in, numpy out)
     def _host_result(self, h: _lib.MeshHost, n: int, copy: bool) -> HostMesh:
