@@ -468,6 +468,50 @@ def main():
             ms = timed(lambda s: m.terrain_mesh(dcoords, 42, GREEDY, out=fout))
             also["fused_terrain_greedy"] = {"chunks_per_s": n_step / (ms * 1e-3), "ms_per_step": ms,
                                             "quads": int(fprobe.total.item())}
+            # the whole north-star path through the host API: chunk coordinates in, host meshes out (terrain is
+            # generated on the device, so only 12 bytes per chunk go up; the mesh download bounds the call)
+            hc = np.ascontiguousarray(coords_np)
+            m.use_stream(None)
+            for _ in range(2):
+                r = m.terrain_mesh_host(hc, 42, mode, copy=False)
+            tw = time.perf_counter()
+            reps = 8
+            for _ in range(reps):
+                r = m.terrain_mesh_host(hc, 42, mode, copy=False)
+            dtw = (time.perf_counter() - tw) / reps
+            also["e2e_from_coords"] = {"chunks_per_s": n_step / dtw, "ms_per_call": dtw * 1e3, "api": "vxp_terrain_mesh_host",
+                                       "h2d_bytes": int(hc.nbytes), "d2h_bytes": int(8 + 8 * n_step + 56 * r.total_quads)}
+            # latency of one voxel edit -> re-meshed chunks, device level (no host round trip inside;
+            # timed with events over back-to-back calls) and host level (edits up, new meshes down, wall clock)
+            from voxelphile_b200 import EDIT_DTYPE
+            surf = int(np.argmax(counts[0]))                                 # a surface chunk of batch 0
+            ed = np.array([(surf, 0, 16, 31, 0)], dtype=EDIT_DTYPE)          # on two faces: three chunks re-meshed
+            ded = torch.from_numpy(ed.view(np.int32).reshape(-1, 3)).to(dev)
+            m.use_current_torch_stream()
+            work = batches[0].clone()
+            for _ in range(5):
+                dl, dcn, dm = m.remesh_edits(work, dnbr, ded, mode)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(200):
+                dl, dcn, dm = m.remesh_edits(work, dnbr, ded, mode)
+            b.record()
+            torch.cuda.synchronize()
+            dev_us = a.elapsed_time(b) / 200 * 1e3
+            m.use_stream(None)
+            hv0 = batches[0].cpu().numpy().view(np.uint16)
+            m.mesh_host(hv0, nbr_np, mode, copy=False)
+            for _ in range(3):
+                m.remesh_edits_host(ed, mode, copy=False)
+            tw = time.perf_counter()
+            for _ in range(200):
+                dirty, hm = m.remesh_edits_host(ed, mode, copy=False)
+            host_us = (time.perf_counter() - tw) / 200 * 1e6
+            m.use_current_torch_stream()
+            also["remesh_one_edit"] = {"device_us": dev_us, "host_us": host_us, "chunks_remeshed": int(len(dirty)),
+                                       "quads": int(hm.total_quads),
+                                       "note": "vxp_remesh_edits / vxp_remesh_edits_host, one edit on a chunk edge"}
 
     # ---------------- CPU baseline: the oracle on this box's host cores (rank 0, N=1 only)
     cpu = None
@@ -489,6 +533,14 @@ def main():
             dtc = time.perf_counter() - tc
             best = dtc if best is None else min(best, dtc)
             reps += 1
+        if "remesh_one_edit" in also:
+            # the same three chunks through the oracle, one thread (what a CPU client would do per edit)
+            k3 = [surf] + [int(nbr_np[surf][f]) for f in (0, 5) if nbr_np[surf][f] >= 0]
+            tc = time.perf_counter()
+            for _ in range(20):
+                for c in k3:
+                    O.mesh_chunk_keys(hv[c], [None if hn[c, f] < 0 else hv[hn[c, f]] for f in range(6)], mode)
+            also["remesh_one_edit"]["cpu_oracle_us"] = (time.perf_counter() - tc) / 20 * 1e6
         cpu = {"value": n_cpu / best, "unit": "chunks/s", "cores": threads, "kind": "port",
                "sample": f"first {n_cpu} chunks of batch 0 (seed 42), best of {reps} passes, "
                          f"in-repo C oracle (scalar, pthreads); the reference has no mesher to time"}
