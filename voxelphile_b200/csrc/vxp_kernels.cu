@@ -317,7 +317,7 @@ cudaError_t launch_mesh_range(const uint16_t* d_voxels, const int32_t* d_nbr6, u
     if (lo >= hi) return cudaSuccess;
     const v4::Bnd bnd{scratch.tags, scratch.planes, scratch.epoch};
     const uint32_t grid = hi - lo;
-    const v4::Chain chain{nullptr, nullptr, nullptr};
+    const v4::Chain chain{nullptr, nullptr, nullptr, 0u, 0u};
     return greedy ? launch_mesh_kernel<true>(grid, 0, stream, d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd, chain)
                   : launch_mesh_kernel<false>(grid, 0, stream, d_voxels, d_nbr6, n, lo, hi, mesh_out(o), bnd, chain);
 }
@@ -331,7 +331,17 @@ cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_
     v4::MeshOut out = mesh_out(o);
     out.total = counter;
     out.cta_inc = v4::kCtaOne;
-    const v4::Chain chain{reinterpret_cast<unsigned long long*>(o.total_quads), nullptr, nullptr};
+    // deal the runs of 16 chunks out with a stride of about 0.618 of their number, coprime to it (see v4::Chain)
+    uint32_t runs = n >> 4, stride = 0;
+    if (runs >= 8 && !getenv("VXP_NO_DEAL")) {
+        auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+        stride = (uint32_t)((unsigned long long)runs * 618u / 1000u) | 1u;
+        while (gcd(stride, runs) != 1u) stride += 2u;
+        stride %= runs;
+    } else {
+        runs = 0;
+    }
+    const v4::Chain chain{reinterpret_cast<unsigned long long*>(o.total_quads), nullptr, nullptr, runs, stride};
     return greedy ? launch_mesh_kernel<true>(n, overlap, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain)
                   : launch_mesh_kernel<false>(n, overlap, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain);
 }
@@ -385,7 +395,7 @@ cudaError_t launch_mesh_list(const uint16_t* d_voxels, const int32_t* d_nbr6, ui
     v4::MeshOut out = mesh_out(o);
     out.total = counter;
     out.cta_inc = v4::kCtaOne;
-    const v4::Chain chain{reinterpret_cast<unsigned long long*>(o.total_quads), d_list, d_count};
+    const v4::Chain chain{reinterpret_cast<unsigned long long*>(o.total_quads), d_list, d_count, 0u, 0u};
     return greedy ? launch_mesh_kernel<true>(max_count, 0, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain)
                   : launch_mesh_kernel<false>(max_count, 0, stream, d_voxels, d_nbr6, n, 0, n, out, bnd, chain);
 }

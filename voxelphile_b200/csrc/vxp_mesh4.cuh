@@ -210,23 +210,37 @@ __device__ __forceinline__ void convert_rows(SM& sm, const uint4* slab, int s, u
                                              IdPlanes& ip) {
     const int tid = threadIdx.x;
     unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
-    uint32_t p0 = 0, p1 = 0, p2 = 0, any = 0;
+    uint32_t p0 = 0, p1 = 0, p2 = 0;
     uint4 q[4];
+    uint32_t slab_or = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int idx = tid + k * kThreads;                 // uint4 index inside the slab: row*4 + piece
-        q[k] = slab[idx];                                   // a warp reads 512 contiguous bytes
-        const int row = s * 256 + (idx >> 2), p = idx & 3;  // row = z*32 + y
-        const uint32_t bits = nz8(q[k]);
-        v_or |= q[k].x | q[k].y | q[k].z | q[k].w;
-        v_and &= q[k].x & q[k].y & q[k].z & q[k].w;
-        o_and &= bits;
-        any |= bits;
-        occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)bits;
+        q[k] = slab[tid + k * kThreads];                    // uint4 index inside the slab: row*4 + piece; a warp reads 512 contiguous bytes
+        slab_or |= q[k].x | q[k].y | q[k].z | q[k].w;
     }
-    if constexpr (kPlanes) {
-        // the warp's 4 x 8 rows of this slab: nothing to pull out of 32 rows of air (their planes are 0)
-        if (__any_sync(kFull, any != 0)) {
+    v_or |= slab_or;
+    // the warp's 4 x 8 rows of this slab.  32 rows of air (38 % of the chunks of a terrain world are nothing else,
+    // and half of every surface chunk) need no bit gathering: zero occupancy, and the flags follow.
+    if (!__any_sync(kFull, slab_or != 0u)) {
+        v_and = 0u;
+        o_and = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + k * kThreads;
+            const int row = s * 256 + (idx >> 2), p = idx & 3;  // row = z*32 + y
+            occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = 0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + k * kThreads;
+            const int row = s * 256 + (idx >> 2), p = idx & 3;
+            const uint32_t bits = nz8(q[k]);
+            v_and &= q[k].x & q[k].y & q[k].z & q[k].w;
+            o_and &= bits;
+            occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)bits;
+        }
+        if constexpr (kPlanes) {
             id_plane_bytes<0>(q[0], p0, p1, p2);
             id_plane_bytes<1>(q[1], p0, p1, p2);
             id_plane_bytes<2>(q[2], p0, p1, p2);
@@ -1188,6 +1202,11 @@ struct Chain {
     // grid is an upper bound of the count, which only the device knows.  nullptr: CTA b meshes chunk chunk0 + b.
     const uint32_t* list;
     const uint32_t* list_count;       // nullptr: the whole grid is the list
+    // Whole-batch launches deal the chunks out in runs of 16 (x neighbours stay next to each other in time, which
+    // the boundary exchange relies on), run g of the grid being run (g * run_stride) % runs of the batch: stored
+    // worlds come sorted by coordinate, and a stride spreads their heavy (surface) and light (air, buried) layers
+    // evenly over the launch instead of sending them through the GPU one after the other.  runs == 0: identity.
+    uint32_t runs, run_stride;
 };
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -1204,7 +1223,10 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
             MeshOut out, Bnd bnd, Chain chain) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<kGreedy>& sm = *reinterpret_cast<Smem<kGreedy>*>(smem_raw);
-    uint32_t chunk = chunk0 + blockIdx.x, mi = chunk;
+    uint32_t chunk = chunk0 + blockIdx.x;
+    if (chain.runs != 0u && (blockIdx.x >> 4) < chain.runs)
+        chunk = (uint32_t)(((unsigned long long)(blockIdx.x >> 4) * chain.run_stride) % chain.runs) * 16u + (blockIdx.x & 15u);
+    uint32_t mi = chunk;
     bool active = chunk < hi;
     if (chain.list != nullptr) {
         active = chain.list_count == nullptr || blockIdx.x < __ldg(chain.list_count);
