@@ -212,23 +212,34 @@ __device__ __forceinline__ void convert_rows(SM& sm, const uint4* slab, int s, u
     unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
     uint32_t p0 = 0, p1 = 0, p2 = 0;
     uint4 q[4];
-    uint32_t slab_or = 0;
+    uint32_t slab_or = 0, slab_and = kFull;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         q[k] = slab[tid + k * kThreads];                    // uint4 index inside the slab: row*4 + piece; a warp reads 512 contiguous bytes
         slab_or |= q[k].x | q[k].y | q[k].z | q[k].w;
+        slab_and &= q[k].x & q[k].y & q[k].z & q[k].w;
     }
     v_or |= slab_or;
-    // the warp's 4 x 8 rows of this slab.  32 rows of air (38 % of the chunks of a terrain world are nothing else,
-    // and half of every surface chunk) need no bit gathering: zero occupancy, and the flags follow.
-    if (!__any_sync(kFull, slab_or != 0u)) {
-        v_and = 0u;
-        o_and = 0u;
+    v_and &= slab_and;
+    // The warp's rows of this slab: 8 values of y in 4 layers.  In a terrain world most of these blocks hold one
+    // value only - air above the surface (38 % of the chunks are nothing else), one kind of rock below it - and
+    // then there is nothing to gather bit by bit: the occupancy bytes and the id planes are all ones or all zeros.
+    const uint32_t id = slab_or & 0xFFFFu;
+    const uint32_t first = __shfl_sync(kFull, slab_or, 0);              // (every lane takes part: not inside the &&)
+    const bool same = slab_or == slab_and && id == (slab_or >> 16) && slab_or == first;
+    if (__all_sync(kFull, same)) {
+        const uint32_t fill = id ? 0xFFu : 0u;
+        o_and &= fill;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int idx = tid + k * kThreads;
             const int row = s * 256 + (idx >> 2), p = idx & 3;  // row = z*32 + y
-            occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = 0;
+            occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)fill;
+        }
+        if constexpr (kPlanes) {
+            p0 = (id & 1u) ? kFull : 0u;
+            p1 = (id & 2u) ? kFull : 0u;
+            p2 = (id & 4u) ? kFull : 0u;
         }
     } else {
 #pragma unroll
@@ -236,7 +247,6 @@ __device__ __forceinline__ void convert_rows(SM& sm, const uint4* slab, int s, u
             const int idx = tid + k * kThreads;
             const int row = s * 256 + (idx >> 2), p = idx & 3;
             const uint32_t bits = nz8(q[k]);
-            v_and &= q[k].x & q[k].y & q[k].z & q[k].w;
             o_and &= bits;
             occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)bits;
         }
