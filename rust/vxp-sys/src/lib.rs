@@ -40,6 +40,17 @@ pub struct vxp_chunk_meta {
     pub quad_count: u32,
 }
 
+/// One voxel edit: voxel (x,y,z) of stored chunk `chunk` becomes `id` (0 = air).  12 bytes.
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct vxp_edit {
+    pub chunk: u32,
+    pub x: u16,
+    pub y: u16,
+    pub z: u16,
+    pub id: u16,
+}
+
 #[repr(C)]
 pub struct vxp_mesh_dev {
     pub verts: *mut u64,
@@ -62,6 +73,7 @@ extern "C" {
     pub fn vxp_ctx_destroy(ctx: *mut vxp_ctx);
     pub fn vxp_ctx_set_stream(ctx: *mut vxp_ctx, cuda_stream: *mut c_void) -> vxp_status;
     pub fn vxp_ctx_reset_stream(ctx: *mut vxp_ctx) -> vxp_status;
+    pub fn vxp_ctx_set_overlap(ctx: *mut vxp_ctx, enabled: c_int) -> vxp_status;
     pub fn vxp_ctx_synchronize(ctx: *mut vxp_ctx) -> vxp_status;
     pub fn vxp_status_str(s: vxp_status) -> *const c_char;
     pub fn vxp_last_error(ctx: *const vxp_ctx) -> *const c_char;
@@ -81,10 +93,18 @@ extern "C" {
     pub fn vxp_terrain_mesh_fused(ctx: *mut vxp_ctx, d_coords: *const vxp_coord, n: u32, seed: u64,
                                   mode: vxp_mode, out: *const vxp_mesh_dev) -> vxp_status;
 
+    pub fn vxp_mesh_list(ctx: *mut vxp_ctx, d_voxels: *const u16, d_nbr6: *const i32, n: u32, d_list: *const u32,
+                         count: u32, mode: vxp_mode, out: *const vxp_mesh_dev) -> vxp_status;
+    pub fn vxp_remesh_edits(ctx: *mut vxp_ctx, d_voxels: *mut u16, d_nbr6: *const i32, n: u32,
+                            d_edits: *const vxp_edit, m: u32, mode: vxp_mode, d_dirty: *mut u32,
+                            d_dirty_count: *mut u32, out: *const vxp_mesh_dev) -> vxp_status;
+
     pub fn vxp_terrain_fill_host(ctx: *mut vxp_ctx, coords: *const vxp_coord, n: u32, seed: u64,
                                  voxels: *mut u16) -> vxp_status;
     pub fn vxp_mesh_chunks_host(ctx: *mut vxp_ctx, voxels: *const u16, nbr6: *const i32, n: u32,
                                 n_stored: u32, mode: vxp_mode, out: *mut vxp_mesh_host) -> vxp_status;
     pub fn vxp_terrain_mesh_host(ctx: *mut vxp_ctx, coords: *const vxp_coord, n: u32, seed: u64,
                                  mode: vxp_mode, out: *mut vxp_mesh_host) -> vxp_status;
+    pub fn vxp_remesh_edits_host(ctx: *mut vxp_ctx, edits: *const vxp_edit, m: u32, mode: vxp_mode,
+                                 out: *mut vxp_mesh_host, dirty: *mut *const u32, count: *mut u32) -> vxp_status;
 }

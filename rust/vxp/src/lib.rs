@@ -116,6 +116,32 @@ impl Mesher {
     }
 }
 
+/// A voxel edit addressed by position in the batch last passed to [`Mesher::mesh`].
+#[derive(Clone, Copy, Debug)]
+pub struct Edit {
+    pub chunk: u32,
+    pub x: u16,
+    pub y: u16,
+    pub z: u16,
+    pub block: u16,
+}
+
+impl Mesher {
+    /// Edit the world that the last `mesh` call left resident on the device and re-mesh what the
+    /// edits invalidate (SPEC §9).  Returns (index of the chunk in that batch, its new mesh) pairs.
+    pub fn remesh(&mut self, edits: &[Edit], mode: MeshMode) -> Result<Vec<(u32, Mesh)>, MeshError> {
+        let raw: Vec<sys::vxp_edit> =
+            edits.iter().map(|e| sys::vxp_edit { chunk: e.chunk, x: e.x, y: e.y, z: e.z, id: e.block }).collect();
+        let mut host = sys::vxp_mesh_host { verts: ptr::null(), indices: ptr::null(), meta: ptr::null(), total_quads: 0 };
+        let (mut dirty, mut count) = (ptr::null::<u32>(), 0u32);
+        check(unsafe {
+            sys::vxp_remesh_edits_host(self.ctx, raw.as_ptr(), raw.len() as u32, mode_of(mode), &mut host, &mut dirty, &mut count)
+        })?;
+        let ids = unsafe { std::slice::from_raw_parts(dirty, count as usize) };
+        Ok(ids.iter().copied().zip(unsafe { split(&host, count as usize) }).collect())
+    }
+}
+
 fn mode_of(m: MeshMode) -> sys::vxp_mode {
     match m {
         MeshMode::Culled => sys::VXP_MODE_CULLED,

@@ -1233,17 +1233,9 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
             MeshOut out, Bnd bnd, Chain chain) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<kGreedy>& sm = *reinterpret_cast<Smem<kGreedy>*>(smem_raw);
-    uint32_t chunk = chunk0 + blockIdx.x;
-    if (chain.runs != 0u && (blockIdx.x >> 4) < chain.runs)
-        chunk = (uint32_t)(((unsigned long long)(blockIdx.x >> 4) * chain.run_stride) % chain.runs) * 16u + (blockIdx.x & 15u);
-    uint32_t mi = chunk;
-    bool active = chunk < hi;
-    if (chain.list != nullptr) {
-        active = chain.list_count == nullptr || blockIdx.x < __ldg(chain.list_count);
-        chunk = active ? __ldg(chain.list + blockIdx.x) : 0u;
-        mi = blockIdx.x;
-        active = active && chunk < n;
-    }
+    const bool dealt = chain.runs != 0u && (blockIdx.x >> 4) < chain.runs;
+    if (dealt && threadIdx.x == 0)              // one 64-bit modulo per CTA, not per thread
+        sm.cursor = (uint32_t)(((unsigned long long)(blockIdx.x >> 4) * chain.run_stride) % chain.runs) * 16u + (blockIdx.x & 15u);
     const bool closer = chain.user_total != nullptr && blockIdx.x == gridDim.x - 1;
     if (threadIdx.x == 0) {
         if (closer) griddep_wait();             // the previous launch has completed (its slot is free for the next one)
@@ -1255,6 +1247,15 @@ mesh_kernel(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr
     }
     __syncthreads();                            // barrier init visible to all
     griddep_launch_dependents();
+    uint32_t chunk = dealt ? sm.cursor : chunk0 + blockIdx.x;
+    uint32_t mi = chunk;
+    bool active = chunk < hi;
+    if (chain.list != nullptr) {
+        active = chain.list_count == nullptr || blockIdx.x < __ldg(chain.list_count);
+        chunk = active ? __ldg(chain.list + blockIdx.x) : 0u;
+        mi = blockIdx.x;
+        active = active && chunk < n;
+    }
 #ifdef VXP_PROFILE
     if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][0] = prof_now();
 #endif
