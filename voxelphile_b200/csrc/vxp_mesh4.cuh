@@ -1213,7 +1213,8 @@ struct Chain {
     const uint32_t* list;
     const uint32_t* list_count;       // nullptr: the whole grid is the list
     // Whole-batch launches deal the chunks out in runs of 16 (x neighbours stay next to each other in time, which
-    // the boundary exchange relies on), run g of the grid being run (g * run_stride) % runs of the batch: stored
+    // the boundary exchange relies on), run g of the grid being run (g * run_stride) % runs of the batch (a small
+    // stride coprime to runs): stored
     // worlds come sorted by coordinate, and a stride spreads their heavy (surface) and light (air, buried) layers
     // evenly over the launch instead of sending them through the GPU one after the other.  runs == 0: identity.
     uint32_t runs, run_stride;
