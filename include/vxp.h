@@ -141,6 +141,21 @@ vxp_status vxp_remesh_edits(vxp_ctx *ctx, uint16_t *d_voxels, const int32_t *d_n
                             const vxp_edit *d_edits, uint32_t m, vxp_mode mode,
                             uint32_t *d_dirty, uint32_t *d_dirty_count, const vxp_mesh_dev *out);
 
+/* ---- chunk wire format (SPEC §10): palette + bit-packed indices ---- */
+/* A packed batch is a byte buffer of 16-byte-aligned records (48-byte header + palette, then 0 / 4 / 8 / 16 / 64 KiB
+ * of indices for 1 / 2 / 3-4 / 5-16 / more distinct ids) plus offsets[i] = byte offset of chunk i's record. */
+#define VXP_PACKED_HEADER_BYTES 48
+#define VXP_PACKED_MAX_RECORD_BYTES (48 + 65536)
+/* Compress n stored chunks on the device.  Records are placed in arbitrary order (d_offsets says where); the bytes
+ * of a record depend on its chunk only.  *d_total_bytes ends as the bytes the batch needs: if that exceeds
+ * capacity_bytes, the records that did not fit have offset UINT64_MAX.  d_packed must be 16-byte aligned. */
+vxp_status vxp_pack_chunks(vxp_ctx *ctx, const uint16_t *d_voxels, uint32_t n, uint8_t *d_packed,
+                           uint64_t capacity_bytes, uint64_t *d_offsets, uint64_t *d_total_bytes);
+/* Expand n records into d_voxels (n * 32768 u16).  Malformed records come out as air and make the NEXT
+ * vxp_ctx_synchronize return VXP_ERR_BAD_ARG. */
+vxp_status vxp_unpack_chunks(vxp_ctx *ctx, const uint8_t *d_packed, const uint64_t *d_offsets, uint32_t n,
+                             uint16_t *d_voxels);
+
 /* ---- host level: host pointers in, context-owned pinned results out ---- */
 vxp_status vxp_terrain_fill_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
                                  uint64_t seed, uint16_t *voxels);
@@ -150,7 +165,13 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx *ctx, const uint16_t *voxels, const int3
                                 uint32_t n, uint32_t n_stored, vxp_mode mode, vxp_mesh_host *out);
 vxp_status vxp_terrain_mesh_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
                                  uint64_t seed, vxp_mode mode, vxp_mesh_host *out);
-/* Edit the world that the last vxp_mesh_chunks_host call left resident on the device (its voxels and neighbour
+/* vxp_mesh_chunks_host for a packed batch: only the packed bytes cross PCIe (9 x fewer for a terrain world), the
+ * chunks are expanded on the device.  n_stored records (the first n are meshed, nbr6 is n x 6 and indexes all of
+ * them); every record is validated here (VXP_ERR_BAD_ARG).  The expanded world stays resident like after
+ * vxp_mesh_chunks_host. */
+vxp_status vxp_mesh_packed_host(vxp_ctx *ctx, const uint8_t *packed, uint64_t packed_bytes, const uint64_t *offsets,
+                                const int32_t *nbr6, uint32_t n, uint32_t n_stored, vxp_mode mode, vxp_mesh_host *out);
+/* Edit the world that the last vxp_mesh_chunks_host / vxp_mesh_packed_host call left resident on the device (its voxels and neighbour
  * table) and re-mesh what the edits invalidate: 12 bytes per edit go up, only the new meshes come down.
  * *dirty (context-owned, pinned, *count entries) names the re-meshed chunks; out->meta[k] belongs to (*dirty)[k].
  * VXP_ERR_BAD_ARG if no world is resident or an edit is out of range. */

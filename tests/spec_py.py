@@ -237,3 +237,52 @@ def apply_edits(vox: np.ndarray, nbr, edits, n_mesh=None) -> list[int]:
                 if 0 <= nb < n:
                     dirty.add(nb)
     return sorted(dirty)
+
+
+# --------------------------------------------------------------------------- SPEC §10 wire format
+PACK_MAGIC = 0x31505856
+
+
+def pack_chunk(vox: np.ndarray) -> bytes:
+    """Canonical record of one chunk (SPEC §10)."""
+    vox = np.ascontiguousarray(vox, dtype=np.uint16).reshape(-1)
+    pal = np.unique(vox)
+    k = len(pal)
+    bits = 16 if k > 16 else 0 if k <= 1 else 1 if k <= 2 else 2 if k <= 4 else 4
+    head = np.zeros(4, dtype=np.uint32)
+    head[0], head[1], head[2] = PACK_MAGIC, bits | ((0 if bits == 16 else k) << 16), 4096 * bits
+    palette = np.zeros(16, dtype=np.uint16)
+    if bits != 16:
+        palette[:k] = pal
+    if bits == 0:
+        data = b""
+    elif bits == 16:
+        data = vox.tobytes()
+    else:
+        idx = np.searchsorted(pal, vox).astype(np.uint64)
+        per = 64 // bits                                    # voxels per u64 word
+        shifts = (np.arange(per, dtype=np.uint64) * np.uint64(bits))
+        data = (idx.reshape(-1, per) << shifts).sum(axis=1, dtype=np.uint64).astype("<u8").tobytes()
+    return head.astype("<u4").tobytes() + palette.astype("<u2").tobytes() + data
+
+
+def unpack_record(rec: bytes) -> np.ndarray:
+    head = np.frombuffer(rec[:16], dtype="<u4")
+    bits, k = int(head[1]) & 0xFFFF, int(head[1]) >> 16
+    assert head[0] == PACK_MAGIC and bits in (0, 1, 2, 4, 16) and head[2] == 4096 * bits
+    palette = np.frombuffer(rec[16:48], dtype="<u2")
+    if bits == 16:
+        assert k == 0
+        return np.frombuffer(rec[48:48 + 65536], dtype="<u2").copy()
+    assert 1 <= k <= 16 and k <= (1 << bits)
+    if bits == 0:
+        return np.full(32768, palette[0], dtype=np.uint16)
+    words = np.frombuffer(rec[48:48 + 4096 * bits], dtype="<u8")
+    per = 64 // bits
+    shifts = (np.arange(per, dtype=np.uint64) * np.uint64(bits))
+    idx = ((words[:, None] >> shifts) & np.uint64((1 << bits) - 1)).reshape(-1)
+    return palette[idx.astype(np.int64)]
+
+
+def record_size(rec_head: bytes) -> int:
+    return 48 + int(np.frombuffer(rec_head[8:12], dtype="<u4")[0])

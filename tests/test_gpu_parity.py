@@ -550,3 +550,97 @@ def test_remesh_needs_a_resident_world():
         assert e.value.kind == "BadArg"
     finally:
         m.close()
+
+
+# --------------------------------------------------------------------------- SPEC §10: chunk wire format
+def _palette_chunks(rng):
+    """Chunks with 1, 2, 3, 4, 5, 16 and 17+ distinct ids (every index width), terrain chunks among them."""
+    chunks = []
+    for k in (1, 2, 3, 4, 5, 9, 16, 17, 300):
+        ids = np.concatenate([[0], np.sort(rng.choice(np.arange(1, 65535), size=k - 1, replace=False))]).astype(np.uint16)
+        v = ids[rng.integers(0, k, 32768)]
+        v[:k] = ids
+        chunks.append(v)
+    chunks.append(np.full(32768, 0xFFFF, np.uint16))
+    from voxelphile_b200 import grid_coords
+    chunks.extend(O.terrain_fill_batch(42, grid_coords((0, 6, 0), (2, 10, 2))))
+    return np.stack(chunks)
+
+
+def test_pack_matches_restatement_and_round_trips(mesher):
+    import torch
+    rng = np.random.default_rng(77)
+    vox = _palette_chunks(rng)
+    n = vox.shape[0]
+    dv = dev(vox.view(np.int16))
+    packed, offsets, total = mesher.pack(dv)
+    back = mesher.unpack(packed, offsets)
+    mesher.synchronize()
+    torch.cuda.synchronize()
+    hp, ho, ht = packed.cpu().numpy(), offsets.cpu().numpy().astype(np.int64), int(total.item())
+    want = [S.pack_chunk(v) for v in vox]
+    assert ht == sum(len(r) for r in want)
+    spans = sorted((int(o), len(r)) for o, r in zip(ho, want))
+    assert spans[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:])), "records must tile the buffer"
+    for i in range(n):
+        assert hp[ho[i]:ho[i] + len(want[i])].tobytes() == want[i], f"record {i}"
+    assert np.array_equal(back.cpu().numpy().view(np.uint16), vox)
+    # capacity contract: what does not fit is marked, the total still says how much is needed
+    packed2, offsets2, total2 = mesher.pack(dv, capacity_bytes=4096)
+    torch.cuda.synchronize()
+    assert int(total2.item()) == ht
+    o2 = offsets2.cpu().numpy().view(np.uint64)
+    assert (o2 == np.uint64(0xFFFFFFFFFFFFFFFF)).any() and all(int(o) + len(want[i]) <= 4096 for i, o in enumerate(o2) if o != np.uint64(0xFFFFFFFFFFFFFFFF))
+
+
+def test_unpack_accepts_any_palette_order_and_rejects_malformed(mesher):
+    import torch
+    from voxelphile_b200 import MeshError
+    vox = np.zeros(32768, np.uint16); vox[::3] = 5; vox[1::7] = 9
+    rec = bytearray(S.pack_chunk(vox))                       # palette [0, 5, 9], 2 bits
+    # swap palette entries 1 and 2 and the indices with them: same chunk, non-canonical record
+    pal = np.frombuffer(bytes(rec[16:48]), dtype="<u2").copy(); pal[[1, 2]] = pal[[2, 1]]
+    data = np.frombuffer(bytes(rec[48:]), dtype=np.uint8)
+    idx = np.stack([(data >> s) & 3 for s in (0, 2, 4, 6)], axis=1).reshape(-1)
+    idx = np.where(idx == 1, 2, np.where(idx == 2, 1, idx)).reshape(-1, 4)
+    data2 = (idx[:, 0] | idx[:, 1] << 2 | idx[:, 2] << 4 | idx[:, 3] << 6).astype(np.uint8)
+    rec2 = bytes(rec[:16]) + pal.tobytes() + data2.tobytes()
+    buf = np.frombuffer(rec2, dtype=np.uint8).copy()
+    got = mesher.unpack(dev(buf), dev(np.zeros(1, np.int64)))
+    mesher.synchronize()
+    assert np.array_equal(got.cpu().numpy().view(np.uint16).reshape(-1), vox)
+    bad = buf.copy(); bad[4] = 3                               # bits = 3 is not a width of the format
+    mesher.unpack(dev(bad), dev(np.zeros(1, np.int64)))
+    with pytest.raises(MeshError) as e:
+        mesher.synchronize()
+    assert e.value.kind == "BadArg"
+    mesher.synchronize()                                       # the verdict is reported once
+    with pytest.raises(MeshError):
+        mesher.mesh_packed_host(bad, np.zeros(1, np.uint64), None, 1)
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_mesh_packed_host_equals_mesh_host(mesher, mode, mname):
+    """Packed upload path: same meshes as the raw upload path, and the world stays resident for edits."""
+    from voxelphile_b200 import grid_coords, neighbour_table
+    coords = grid_coords((0, 5, 0), (5, 11, 5))               # 150 chunks: air, surface and buried ones
+    nbr = neighbour_table(coords)
+    vox = O.terrain_fill_batch(42, coords)
+    recs = [S.pack_chunk(v) for v in vox]
+    order = np.random.default_rng(1).permutation(len(recs))   # records in arbitrary order
+    offsets = np.zeros(len(recs), np.uint64)
+    pos = 0
+    for i in order:
+        offsets[i] = pos
+        pos += len(recs[i])
+    buf = np.zeros(pos, np.uint8)
+    for i in range(len(recs)):
+        buf[int(offsets[i]):int(offsets[i]) + len(recs[i])] = np.frombuffer(recs[i], np.uint8)
+    assert pos < vox.nbytes / 4
+    a = mesher.mesh_packed_host(buf, offsets, nbr, mode)
+    want_hash, want_cnt = O.mesh_batch_hash(vox, nbr, mode)
+    assert np.array_equal(a.meta[:, 1], want_cnt) and np.array_equal(_chunk_hashes(a), want_hash)
+    edits, rows = _random_edits(np.random.default_rng(3), len(coords), 10)
+    dirty, host = mesher.remesh_edits_host(edits, mode)
+    assert sorted(dirty.tolist()) == S.apply_edits(vox, nbr, rows)
+    _check_remeshed(host, dirty.astype(np.int64), vox, nbr, mode)

@@ -61,6 +61,10 @@ SIGNATURES = {
                          C.c_void_p, C.c_void_p, C.POINTER(MeshDev)]),
     "vxp_remesh_edits_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(MeshHost),
                               C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
+    "vxp_pack_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "vxp_unpack_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "vxp_mesh_packed_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                             C.c_int, C.POINTER(MeshHost)]),
     "vxp_terrain_fill_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]),
     "vxp_mesh_chunks_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                              C.POINTER(MeshHost)]),

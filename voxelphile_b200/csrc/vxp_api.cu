@@ -44,6 +44,10 @@ struct vxp_ctx {
     uint32_t* d_dirty_count = nullptr;
     uint32_t* h_dirty = nullptr;        size_t h_dirty_cap = 0;
     uint32_t* h_dirty_count = nullptr;
+    // wire format: unpack status word (device + pinned copy) and the host-level call's upload arenas
+    uint32_t* d_status = nullptr;       uint32_t* h_status = nullptr;   bool status_pending = false;
+    unsigned char* d_packed = nullptr;  size_t packed_cap = 0;          // bytes
+    unsigned long long* d_offsets = nullptr;  size_t offsets_cap = 0;   // chunks
     cudaEvent_t ev_chain = nullptr;
     // column scratch of the fused terrain+mesh path (vxp_launch.h: ColumnScratch)
     unsigned char* d_columns = nullptr;  size_t columns_cap = 0;   // chunks
@@ -313,6 +317,8 @@ vxp_status vxp_ctx_create(int device, vxp_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_dirty_count), sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_dirty_count), sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_status), sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_total), sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_totals), vxp_ctx::kMaxSlices * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
@@ -355,6 +361,10 @@ void vxp_ctx_destroy(vxp_ctx* ctx) {
     cudaFree(ctx->d_dirty_count);
     cudaFreeHost(ctx->h_dirty);
     cudaFreeHost(ctx->h_dirty_count);
+    cudaFree(ctx->d_status);
+    cudaFreeHost(ctx->h_status);
+    cudaFree(ctx->d_packed);
+    cudaFree(ctx->d_offsets);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     cudaFreeHost(ctx->h_meta);
     cudaFreeHost(ctx->h_verts);
@@ -396,6 +406,11 @@ vxp_status vxp_ctx_synchronize(vxp_ctx* ctx) {
     DeviceGuard g(ctx->device);
     VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->chain_open = false;
+    if (ctx->status_pending) {           // a vxp_unpack_chunks call since the last synchronize: did it meet a malformed record?
+        ctx->status_pending = false;
+        VXP_CUDA(ctx, cudaMemcpy(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (*ctx->h_status) return VXP_ERR_BAD_ARG;
+    }
     return VXP_OK;
 }
 
@@ -566,6 +581,36 @@ vxp_status vxp_remesh_edits(vxp_ctx* ctx, uint16_t* d_voxels, const int32_t* d_n
     return VXP_OK;
 }
 
+// ------------------------------------------------------------------ chunk wire format (SPEC §10)
+
+vxp_status vxp_pack_chunks(vxp_ctx* ctx, const uint16_t* d_voxels, uint32_t n, uint8_t* d_packed, uint64_t capacity_bytes,
+                           uint64_t* d_offsets, uint64_t* d_total_bytes) {
+    if (!ctx || !d_total_bytes || (n && (!d_voxels || !aligned16(d_voxels) || !d_offsets))) return VXP_ERR_BAD_ARG;
+    if (capacity_bytes && (!d_packed || !aligned16(d_packed))) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    ctx->chain_open = false;
+    VXP_CUDA(ctx, vxp::launch_pack_chunks(d_voxels, n, d_packed, capacity_bytes, reinterpret_cast<unsigned long long*>(d_offsets),
+                                          reinterpret_cast<unsigned long long*>(d_total_bytes), ctx->stream));
+    ctx->launches += n ? 1 : 0;
+    return VXP_OK;
+}
+
+vxp_status vxp_unpack_chunks(vxp_ctx* ctx, const uint8_t* d_packed, const uint64_t* d_offsets, uint32_t n, uint16_t* d_voxels) {
+    if (!ctx || (n && (!d_packed || !aligned16(d_packed) || !d_offsets || !d_voxels || !aligned16(d_voxels)))) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    ctx->chain_open = false;
+    if (ctx->status_pending) {           // keep an earlier call's verdict: fold it in before the word is zeroed again
+        VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        VXP_CUDA(ctx, cudaMemcpy(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (*ctx->h_status) { ctx->status_pending = false; return VXP_ERR_BAD_ARG; }
+    }
+    VXP_CUDA(ctx, vxp::launch_unpack_chunks(d_packed, reinterpret_cast<const unsigned long long*>(d_offsets), n, d_voxels,
+                                            ctx->d_status, ctx->stream));
+    ctx->launches += n ? 1 : 0;
+    ctx->status_pending = n != 0;
+    return VXP_OK;
+}
+
 // ------------------------------------------------------------------ host level
 
 vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t n, uint64_t seed,
@@ -722,6 +767,55 @@ vxp_status vxp_terrain_mesh_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
             if (n && column_scratch(ctx, n, &cols) != VXP_OK) return cudaErrorMemoryAllocation;
             ctx->launches += n ? 1 : 0;
             return vxp::launch_terrain_mesh(ctx->d_coords, n, seed, mode == VXP_MODE_GREEDY, dev, cols, ctx->stream);
+        },
+        out);
+}
+
+namespace {
+bool valid_record(const uint8_t* packed, uint64_t packed_bytes, uint64_t off) {
+    if ((off & 15u) || off > packed_bytes || packed_bytes - off < VXP_PACKED_HEADER_BYTES) return false;
+    uint32_t h[3];
+    std::memcpy(h, packed + off, sizeof h);
+    const uint32_t bits = h[1] & 0xFFFFu, len = h[1] >> 16;
+    if (h[0] != 0x31505856u || h[2] != 4096u * bits) return false;
+    if (!(bits == 0 || bits == 1 || bits == 2 || bits == 4 || bits == 16)) return false;
+    if (bits == 16 ? len != 0 : (len < 1 || len > 16 || len > (1u << bits))) return false;
+    return packed_bytes - off - VXP_PACKED_HEADER_BYTES >= h[2];
+}
+}  // namespace
+
+vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t packed_bytes, const uint64_t* offsets,
+                                const int32_t* nbr6, uint32_t n, uint32_t n_stored, vxp_mode mode, vxp_mesh_host* out) {
+    if (!ctx || !out || !valid_mode(mode) || n_stored < n || (n_stored && (!packed || !offsets))) return VXP_ERR_BAD_ARG;
+    for (uint32_t i = 0; i < n_stored; ++i)
+        if (!valid_record(packed, packed_bytes, offsets[i])) return VXP_ERR_BAD_ARG;
+    if (nbr6)
+        for (size_t i = 0; i < (size_t)n * 6; ++i)
+            if (nbr6[i] < -1 || nbr6[i] >= (int64_t)n_stored) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    vxp_status s;
+    if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n_stored, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
+    if ((s = grow_device(ctx, &ctx->d_nbr6, &ctx->nbr_cap, n, 6)) != VXP_OK) return s;
+    if ((s = grow_device(ctx, &ctx->d_packed, &ctx->packed_cap, (size_t)packed_bytes + 16, 1)) != VXP_OK) return s;
+    if ((s = grow_device(ctx, &ctx->d_offsets, &ctx->offsets_cap, n_stored, 1)) != VXP_OK) return s;
+    if ((s = join_chain(ctx)) != VXP_OK) return s;
+    ctx->world_n = n;
+    ctx->world_stored = n_stored;
+    ctx->world_has_nbr = nbr6 != nullptr;
+    ctx->world_valid = n > 0;
+    const int32_t* d_nbr = nbr6 ? ctx->d_nbr6 : nullptr;
+    if (n_stored) {
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_packed, packed, packed_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, offsets, (size_t)n_stored * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (nbr6) VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        VXP_CUDA(ctx, vxp::launch_unpack_chunks(ctx->d_packed, ctx->d_offsets, n_stored, ctx->d_voxels, ctx->d_status, ctx->stream));
+        ctx->launches += 1;
+    }
+    const int greedy = mode == VXP_MODE_GREEDY;
+    return mesh_into_host(
+        ctx, n,
+        [&](const vxp_mesh_dev& dev) {
+            return chained_mesh_launch(ctx, ctx->d_voxels, d_nbr, n, greedy, dev) == VXP_OK ? cudaSuccess : cudaErrorUnknown;
         },
         out);
 }

@@ -263,6 +263,51 @@ class Mesher:
             dirty = np.empty(0, np.uint32)
         return dirty, self._host_result(h, k, copy)
 
+    # ------------------------------------------------------------ chunk wire format (SPEC §10)
+    def pack(self, voxels: "torch.Tensor", capacity_bytes: Optional[int] = None):
+        """vxp_pack_chunks: (packed uint8 tensor, offsets int64 tensor [n], total-bytes int64 tensor [1]); async."""
+        import torch
+        n = voxels.shape[0]
+        cap = n * (48 + 65536) if capacity_bytes is None else capacity_bytes
+        packed = torch.empty(max(cap, 16), dtype=torch.uint8, device=voxels.device)
+        offsets = torch.empty(max(n, 1), dtype=torch.int64, device=voxels.device)
+        total = torch.zeros(1, dtype=torch.int64, device=voxels.device)
+        self._check(self._lib.vxp_pack_chunks(self._h, voxels.data_ptr(), n, packed.data_ptr(), cap, offsets.data_ptr(),
+                                              total.data_ptr()))
+        return packed, offsets[:n], total
+
+    def unpack(self, packed: "torch.Tensor", offsets: "torch.Tensor", out: Optional["torch.Tensor"] = None) -> "torch.Tensor":
+        """vxp_unpack_chunks: int16 [n, 32768]; a malformed record surfaces at the next synchronize()."""
+        import torch
+        n = int(offsets.shape[0])
+        if out is None:
+            out = torch.empty((n, CHUNK_VOXELS), dtype=torch.int16, device=packed.device)
+        self._check(self._lib.vxp_unpack_chunks(self._h, packed.data_ptr(), offsets.data_ptr(), n, out.data_ptr()))
+        return out
+
+    def mesh_packed_host(self, packed: np.ndarray, offsets: np.ndarray, nbr6: Optional[np.ndarray], mode: int,
+                         copy: bool = True, n_mesh: Optional[int] = None) -> HostMesh:
+        """vxp_mesh_packed_host: packed host bytes in, host mesh out."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_stored = offsets.shape[0]
+        n = n_stored if n_mesh is None else n_mesh
+        nptr = None
+        if nbr6 is not None:
+            nbr6 = np.ascontiguousarray(nbr6, dtype=np.int32).reshape(n, 6)
+            nptr = nbr6.ctypes.data
+        h = _lib.MeshHost()
+        self._check(self._lib.vxp_mesh_packed_host(self._h, packed.ctypes.data, packed.nbytes, offsets.ctypes.data, nptr,
+                                                   n, n_stored, mode, C.byref(h)))
+        return self._host_result(h, n, copy)
+
+    def mesh_packed_host_ptr(self, packed_ptr: int, packed_bytes: int, offsets_ptr: int, nbr6_ptr: Optional[int], n: int,
+                             mode: int) -> HostMesh:
+        h = _lib.MeshHost()
+        self._check(self._lib.vxp_mesh_packed_host(self._h, packed_ptr, packed_bytes, offsets_ptr, nbr6_ptr, n, n, mode,
+                                                   C.byref(h)))
+        return self._host_result(h, n, copy=False)
+
     # ------------------------------------------------------------ host level (numpy in, numpy out)
     def _host_result(self, h: _lib.MeshHost, n: int, copy: bool) -> HostMesh:
         q = int(h.total_quads)
