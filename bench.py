@@ -481,6 +481,38 @@ def main():
             dtw = (time.perf_counter() - tw) / reps
             also["e2e_from_coords"] = {"chunks_per_s": n_step / dtw, "ms_per_call": dtw * 1e3, "api": "vxp_terrain_mesh_host",
                                        "h2d_bytes": int(hc.nbytes), "d2h_bytes": int(8 + 8 * n_step + 56 * r.total_quads)}
+            # the same batch through the packed upload path (SPEC §10): pack once on the device (outside
+            # the timed region, as a server that stores chunks packed would have them), then time host packed bytes in,
+            # host meshes out; plus the pack / unpack kernels on their own (bytes of raw voxels per second)
+            import ctypes as C2
+            m.use_current_torch_stream()
+            pk, po, pt = m.pack(batches[0])
+            torch.cuda.synchronize()
+            pbytes = int(pt.item())
+            pp, op = C2.c_void_p(), C2.c_void_p()
+            assert m._lib.vxp_host_alloc(pbytes, C2.byref(pp)) == 0 and m._lib.vxp_host_alloc(8 * n_step, C2.byref(op)) == 0
+            np.frombuffer((C2.c_char * pbytes).from_address(pp.value), dtype=np.uint8)[:] = pk[:pbytes].cpu().numpy()
+            np.frombuffer((C2.c_char * (8 * n_step)).from_address(op.value), dtype=np.int64)[:] = po.cpu().numpy()
+            hn2 = np.ascontiguousarray(nbr_np)
+            m.use_stream(None)
+            for _ in range(3):
+                r = m.mesh_packed_host_ptr(pp.value, pbytes, op.value, hn2.ctypes.data, n_step, mode)
+            tw = time.perf_counter()
+            for _ in range(8):
+                r = m.mesh_packed_host_ptr(pp.value, pbytes, op.value, hn2.ctypes.data, n_step, mode)
+            dtw = (time.perf_counter() - tw) / 8
+            m.use_current_torch_stream()
+            ms_pack = timed(lambda s: m.pack(batches[s % len(batches)]), steps=20)
+            unp = torch.empty_like(batches[0])
+            ms_unpack = timed(lambda s: m.unpack(pk, po, out=unp), steps=40)
+            m.synchronize()
+            also["e2e_packed"] = {"chunks_per_s": n_step / dtw, "ms_per_call": dtw * 1e3, "api": "vxp_mesh_packed_host",
+                                  "h2d_bytes": int(pbytes + 8 * n_step + hn2.nbytes), "raw_bytes": n_step * CHUNK_BYTES,
+                                  "d2h_bytes": int(8 + 8 * n_step + 56 * r.total_quads),
+                                  "pack_kernel_ms": ms_pack, "unpack_kernel_ms": ms_unpack,
+                                  "unpack_raw_gbs": n_step * CHUNK_BYTES / (ms_unpack * 1e-3) / 1e9}
+            m._lib.vxp_host_free(pp)
+            m._lib.vxp_host_free(op)
             # latency of one voxel edit -> re-meshed chunks, device level (no host round trip inside;
             # timed with events over back-to-back calls) and host level (edits up, new meshes down, wall clock)
             from voxelphile_b200 import EDIT_DTYPE

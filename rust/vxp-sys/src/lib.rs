@@ -99,12 +99,20 @@ extern "C" {
                             d_edits: *const vxp_edit, m: u32, mode: vxp_mode, d_dirty: *mut u32,
                             d_dirty_count: *mut u32, out: *const vxp_mesh_dev) -> vxp_status;
 
+    pub fn vxp_pack_chunks(ctx: *mut vxp_ctx, d_voxels: *const u16, n: u32, d_packed: *mut u8, capacity_bytes: u64,
+                           d_offsets: *mut u64, d_total_bytes: *mut u64) -> vxp_status;
+    pub fn vxp_unpack_chunks(ctx: *mut vxp_ctx, d_packed: *const u8, d_offsets: *const u64, n: u32,
+                             d_voxels: *mut u16) -> vxp_status;
+
     pub fn vxp_terrain_fill_host(ctx: *mut vxp_ctx, coords: *const vxp_coord, n: u32, seed: u64,
                                  voxels: *mut u16) -> vxp_status;
     pub fn vxp_mesh_chunks_host(ctx: *mut vxp_ctx, voxels: *const u16, nbr6: *const i32, n: u32,
                                 n_stored: u32, mode: vxp_mode, out: *mut vxp_mesh_host) -> vxp_status;
     pub fn vxp_terrain_mesh_host(ctx: *mut vxp_ctx, coords: *const vxp_coord, n: u32, seed: u64,
                                  mode: vxp_mode, out: *mut vxp_mesh_host) -> vxp_status;
+    pub fn vxp_mesh_packed_host(ctx: *mut vxp_ctx, packed: *const u8, packed_bytes: u64, offsets: *const u64,
+                                nbr6: *const i32, n: u32, n_stored: u32, mode: vxp_mode,
+                                out: *mut vxp_mesh_host) -> vxp_status;
     pub fn vxp_remesh_edits_host(ctx: *mut vxp_ctx, edits: *const vxp_edit, m: u32, mode: vxp_mode,
                                  out: *mut vxp_mesh_host, dirty: *mut *const u32, count: *mut u32) -> vxp_status;
 }

@@ -61,22 +61,6 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 
 // ---------------------------------------------------------------- u16 -> bit tricks
 
-// bit 15 / bit 31 of the result are set iff the low / high u16 of r is non-zero
-// (other bits are garbage).  No carry crosses the halves: 0x7FFF+0x7FFF < 0x10000.
-__device__ __forceinline__ uint32_t nz_flags(uint32_t r) {
-    return ((r & 0x7FFF7FFFu) + 0x7FFF7FFFu) | r;
-}
-// 4 flag bytes (bit 7 of each) -> 4-bit nibble.  v: garbage allowed outside bit 7 of each byte.
-__device__ __forceinline__ uint32_t gather_bit7(uint32_t v) {
-    return (((v >> 7) & 0x01010101u) * 0x01020408u) >> 24;
-}
-// q holds 8 consecutive u16; bit j of the result = (element j != 0)
-__device__ __forceinline__ uint32_t nonzero8(uint4 q) {
-    uint32_t a = nz_flags(q.x), b = nz_flags(q.y), c = nz_flags(q.z), d = nz_flags(q.w);
-    uint32_t lo = __byte_perm(a, b, 0x7531); // bytes a.1 a.3 b.1 b.3  (the bytes holding bits 15 / 31)
-    uint32_t hi = __byte_perm(c, d, 0x7531);
-    return gather_bit7(lo) | (gather_bit7(hi) << 4);
-}
 __device__ __forceinline__ uint4 xor4(uint4 a, uint4 b) {
     return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w);
 }
@@ -229,6 +213,8 @@ __device__ __forceinline__ void terrain_lattice_fill(TerrainLattice& L, const Te
 __device__ __forceinline__ int lattice_dot(short g, int ax, int az) {
     return (int)(signed char)(g & 0xFF) * ax + (int)(g >> 8) * az;
 }
+// The same dot product as one IDP.2A: `axz` holds (ax, az) as two int16 (ax low), g has gx in byte 0 and gz in byte 1.
+__device__ __forceinline__ int lattice_dot2(unsigned short g, uint32_t axz) { return __dp2a_lo((int)axz, (int)(uint32_t)g, 0); }
 __device__ __forceinline__ int terrain_height_lattice(const TerrainLattice& L, int X, int Z) {
     long long sum = 0;
 #pragma unroll
@@ -239,10 +225,12 @@ __device__ __forceinline__ int terrain_height_lattice(const TerrainLattice& L, i
         const int i = (Xo >> S) - L.ix0[o], j = (Zo >> S) - L.iz0[o];
         const int dx = (Xo & ((1 << S) - 1)) << (8 - S);
         const int dz = (Zo & ((1 << S) - 1)) << (8 - S);
-        const int d00 = lattice_dot(L.g[o][i][j], dx, dz);
-        const int d10 = lattice_dot(L.g[o][i + 1][j], dx - 256, dz);
-        const int d01 = lattice_dot(L.g[o][i][j + 1], dx, dz - 256);
-        const int d11 = lattice_dot(L.g[o][i + 1][j + 1], dx - 256, dz - 256);
+        // (dx, dz) as two int16 in one word; dx - 256 is dx + 0xFF00 in 16 bits (0 <= dx < 256: no carry out of the half)
+        const uint32_t a00 = (uint32_t)dx | (uint32_t)dz << 16;
+        const int d00 = lattice_dot2((unsigned short)L.g[o][i][j], a00);
+        const int d10 = lattice_dot2((unsigned short)L.g[o][i + 1][j], a00 + 0x0000FF00u);
+        const int d01 = lattice_dot2((unsigned short)L.g[o][i][j + 1], a00 + 0xFF000000u);
+        const int d11 = lattice_dot2((unsigned short)L.g[o][i + 1][j + 1], a00 + 0xFF00FF00u);
         const int fx = fade16(dx), fz = fade16(dz);
         const int n0 = d00 * 65536 + fx * (d10 - d00);
         const int n1 = d01 * 65536 + fx * (d11 - d01);

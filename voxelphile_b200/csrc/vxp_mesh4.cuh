@@ -127,7 +127,6 @@ struct __align__(128) Smem {
     uint32_t occ[34 * 34];      // occ[(z+1)*34 + (y+1)], bit x; rows/layers -1 and 32 are the halo
     uint32_t xh[2][32];         // xh[0][z] bit y: voxel (-1,y,z) solid;  xh[1][z] bit y: voxel (32,y,z)
     uint32_t actz[32];          // actz[z] bit y: row (y,z) carries at least one visible face
-    uint32_t wred[kWarps][4];
     uint32_t scratch[kWarps + 1];
     uint32_t seg[192];          // greedy: first log entry of each plane
     uint32_t rows[192];         // greedy: visited rows of each plane
@@ -417,15 +416,6 @@ __device__ __forceinline__ bool halo_finish(SM& sm, const uint16_t* __restrict__
     sm.xh[f][lane] = word;
     return word != kFull;
 }
-template <class SM>
-__device__ __forceinline__ bool load_halo(SM& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n,
-                                          const Bnd& bnd, const HaloRows& rows, Prof& prof) {
-    XPoll xp;
-    const bool a = halo_begin(sm, nb, n, bnd, rows, xp);
-    const bool b = halo_finish(sm, voxels, nb, n, bnd, xp, prof);
-    return a || b;
-}
-
 // ------------------------------------------------------------------ active rows
 // actz[z] bit y = row (y,z) has a solid voxel with an air neighbour (halo included).
 template <bool kGreedy>

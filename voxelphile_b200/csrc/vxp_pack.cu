@@ -109,10 +109,13 @@ __global__ void __launch_bounds__(kThreads) pack_chunks_kernel(const uint16_t* _
         if (bits == 16u) { reinterpret_cast<uint4*>(data)[j] = q; continue; }
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
         uint32_t out = 0;
+        // chunks are mostly runs of one id: look an id up only when it differs from the previous voxel's
+        uint32_t lastv = w[0] & 0xFFFFu, lasti = palette_index(sh.palette, len, lastv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            out |= palette_index(sh.palette, len, w[e] & 0xFFFFu) << (bits * (2 * e));
-            out |= palette_index(sh.palette, len, w[e] >> 16) << (bits * (2 * e + 1));
+        for (int t = 0; t < 8; ++t) {
+            const uint32_t v = (t & 1) ? w[t >> 1] >> 16 : w[t >> 1] & 0xFFFFu;
+            if (v != lastv) { lastv = v; lasti = palette_index(sh.palette, len, v); }
+            out |= lasti << (bits * t);
         }
         if (bits == 1u) data[j] = (unsigned char)out;
         else if (bits == 2u) reinterpret_cast<unsigned short*>(data)[j] = (unsigned short)out;
