@@ -7,6 +7,7 @@
 
 #include "vxp_launch.h"
 #include "vxp_mesh4.cuh"
+#include "vxp_mesh5.cuh"
 
 namespace vxp {
 
@@ -270,6 +271,7 @@ static cudaError_t set_smem(K fn, size_t bytes) {
 cudaError_t configure_device() {
     cudaError_t e = set_smem(v4::mesh_kernel<false>, sizeof(v4::Smem<false>));
     if (e == cudaSuccess) e = set_smem(v4::mesh_kernel<true>, sizeof(v4::Smem<true>));
+    if (e == cudaSuccess) e = set_smem(v5::mesh_kernel_g, sizeof(v5::SmemG));
     if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel<false>, sizeof(v4::Smem<false>));
     if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel<true>, sizeof(v4::Smem<true>));
     return e;
@@ -294,6 +296,11 @@ static v4::MeshOut mesh_out(const vxp_mesh_dev& o) {
                        reinterpret_cast<unsigned long long*>(o.total_quads), o.capacity_quads, 0ull};
 }
 
+// Greedy batches run generation 5 (four CTAs per SM, vxp_mesh5.cuh); VXP_GREEDY_V4=1 selects generation 4 for A/B runs.
+static bool greedy_v4() {
+    static const bool v = getenv("VXP_GREEDY_V4") != nullptr;
+    return v;
+}
 template <bool kGreedy>
 static cudaError_t launch_mesh_kernel(uint32_t grid, int overlap, cudaStream_t stream, const uint16_t* d_voxels,
                                       const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi, v4::MeshOut out, v4::Bnd bnd,
@@ -301,13 +308,15 @@ static cudaError_t launch_mesh_kernel(uint32_t grid, int overlap, cudaStream_t s
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = sizeof(v4::Smem<kGreedy>);
+    const bool g5 = kGreedy && !greedy_v4();
+    cfg.dynamicSmemBytes = g5 ? sizeof(v5::SmemG) : sizeof(v4::Smem<kGreedy>);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
+    if (g5) return cudaLaunchKernelEx(&cfg, v5::mesh_kernel_g, d_voxels, d_nbr6, n, lo, hi, out, bnd, chain);
     return cudaLaunchKernelEx(&cfg, v4::mesh_kernel<kGreedy>, d_voxels, d_nbr6, n, lo, hi, out, bnd, chain);
 }
 
@@ -414,11 +423,11 @@ extern "C" int vxp_debug_occupancy(int greedy, int fused) {
         e = greedy ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, terrain_mesh_kernel<true>, kThreads, sizeof(v4::Smem<true>))
                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, terrain_mesh_kernel<false>, kThreads, sizeof(v4::Smem<false>));
     else
-        e = greedy ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v4::mesh_kernel<true>, kThreads, sizeof(v4::Smem<true>))
+        e = greedy ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v5::mesh_kernel_g, kThreads, sizeof(v5::SmemG))
                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v4::mesh_kernel<false>, kThreads, sizeof(v4::Smem<false>));
     return e == cudaSuccess ? n : -1;
 }
-extern "C" int vxp_debug_smem_bytes(int greedy) { return greedy ? (int)sizeof(v4::Smem<true>) : (int)sizeof(v4::Smem<false>); }
+extern "C" int vxp_debug_smem_bytes(int greedy) { return greedy ? (int)sizeof(v5::SmemG) : (int)sizeof(v4::Smem<false>); }
 
 #ifdef VXP_PROFILE
 extern "C" int vxp_debug_read_prof_time(unsigned long long* out, int max_ctas) {

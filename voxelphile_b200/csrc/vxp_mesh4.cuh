@@ -418,8 +418,8 @@ __device__ __forceinline__ bool halo_finish(SM& sm, const uint16_t* __restrict__
 }
 // ------------------------------------------------------------------ active rows
 // actz[z] bit y = row (y,z) has a solid voxel with an air neighbour (halo included).
-template <bool kGreedy>
-__device__ __forceinline__ void build_active(Smem<kGreedy>& sm) {
+template <class SM>
+__device__ __forceinline__ void build_active(SM& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
