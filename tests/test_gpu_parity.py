@@ -195,12 +195,15 @@ def test_terrain_block_stored_path(mesher, mode, mname):
     check_against_oracle(out.to_host(), vox, nbr, mode)
 
 
-@pytest.mark.parametrize("mode,mname", MODES)
-def test_fused_terrain_mesh(mesher, mode, mname):
-    """Fused path: neighbours are the infinite terrain itself."""
+@pytest.mark.parametrize("mode,mname", MODES + [(1, "greedy_generation5")])
+def test_fused_terrain_mesh(mesher, mode, mname, monkeypatch):
+    """Fused path: neighbours are the infinite terrain itself.  Large greedy batches run the four-CTA kernel
+    (generation 5); VXP_FUSED_V5 selects it for this small one too."""
     import torch
     from voxelphile_b200 import grid_coords
     seed = 42
+    if mname == "greedy_generation5":
+        monkeypatch.setenv("VXP_FUSED_V5", "1")
     coords = np.concatenate([grid_coords((0, 6, 0), (3, 10, 2)), np.array([[-7, 8, 3], [5, 0, 5], [5, 30, 5]], np.int32)])
     out = mesher.terrain_mesh(dev(coords), seed, mode, capacity=coords.shape[0] * 8192)
     torch.cuda.synchronize()
@@ -644,3 +647,28 @@ def test_mesh_packed_host_equals_mesh_host(mesher, mode, mname):
     dirty, host = mesher.remesh_edits_host(edits, mode)
     assert sorted(dirty.tolist()) == S.apply_edits(vox, nbr, rows)
     _check_remeshed(host, dirty.astype(np.int64), vox, nbr, mode)
+
+
+def test_fused_world_generation5_matches_generation4(mesher, monkeypatch):
+    """A batch large enough for the four-CTA fused kernel (32 768 chunks): per-chunk counts and key hashes equal
+    those of the same call forced through the small-batch kernel in slices, and the oracle on sampled chunks."""
+    import torch
+    from voxelphile_b200 import grid_coords
+    coords = grid_coords((-16, -8, -16), (16, 24, 16))
+    assert coords.shape[0] == 32768
+    big = mesher.terrain_mesh(dev(coords), 42, 1, capacity=4_000_000)
+    torch.cuda.synchronize()
+    hb = big.to_host()
+    hashes = _chunk_hashes(hb)
+    for lo in range(0, 32768, 8192):                              # 8192 < 32768: generation 4
+        part = mesher.terrain_mesh(dev(coords[lo:lo + 8192]), 42, 1, capacity=2_000_000)
+        torch.cuda.synchronize()
+        hp = part.to_host()
+        assert np.array_equal(hp.meta[:, 1], hb.meta[lo:lo + 8192, 1])
+        assert np.array_equal(_chunk_hashes(hp), hashes[lo:lo + 8192])
+    surface = np.nonzero(hb.meta[:, 1])[0]
+    for i in surface[:: max(1, len(surface) // 12)]:
+        c = tuple(map(int, coords[i]))
+        nbs = [O.terrain_fill(42, c[0] + d[0], c[1] + d[1], c[2] + d[2]) for d in S.DIRS]
+        want = O.mesh_chunk_keys(O.terrain_fill(42, *c), nbs, 1)
+        assert np.array_equal(np.sort(S.keys_from_verts(hb.chunk(int(i))[0])), want), c

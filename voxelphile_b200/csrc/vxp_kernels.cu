@@ -261,6 +261,95 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, ColumnScra
     }
 }
 
+// ---- generation 5 of the fused greedy kernel (vxp_mesh5.cuh: four CTAs per SM): the chunk is generated one
+// 16 KiB slab at a time into the ring and converted from there, the rest is v5's pipeline.
+__device__ __forceinline__ void terrain_mesh_chunk_g(v5::SmemG& sm, short* s_h, const vxp_coord* __restrict__ coords,
+                                                     const ColumnScratch& cs, uint32_t chunk, const v4::MeshOut& out) {
+    const int tid = threadIdx.x;
+    const vxp_coord c = coords[chunk];
+    v4::Prof prof;
+    prof.start(false);
+    const short* col = cs.heights + (size_t)cs.id_of_slot[cs.slot_of_chunk[chunk]] * kColStride;
+    const int Y0 = 32 * c.y;
+    if (tid == 0) { sm.ones = kFull; sm.zero = 0u; }
+    for (int i = tid; i < 34 * 34 / 2; i += kThreads)
+        reinterpret_cast<uint32_t*>(s_h)[i] = __ldg(reinterpret_cast<const uint32_t*>(col) + i);
+    __syncthreads();
+    // halo occupancy straight from the heights (solid iff Y <= h)
+    for (int i = tid; i < 128; i += kThreads) {       // Y and Z halo rows: word over x
+        const int face = i >> 5, r = i & 31;          // 0:-Y 1:+Y 2:-Z 3:+Z
+        int zz, Y, dst;
+        if (face == 0) { zz = r; Y = Y0 - 1; dst = (r + 1) * 34 + 0; }
+        else if (face == 1) { zz = r; Y = Y0 + 32; dst = (r + 1) * 34 + 33; }
+        else if (face == 2) { zz = -1; Y = Y0 + r; dst = 0 * 34 + (r + 1); }
+        else { zz = 32; Y = Y0 + r; dst = 33 * 34 + (r + 1); }
+        const short* hp = s_h + (zz + 1) * 34 + 1;
+        uint32_t bits = 0;
+#pragma unroll 8
+        for (int x = 0; x < 32; ++x) bits |= (uint32_t)(Y <= hp[x]) << x;
+        sm.occ[dst] = bits;
+    }
+    if (tid < 64) {                                   // X halos: word over y for each z
+        const int face = tid >> 5, z = tid & 31;
+        const int h = s_h[(z + 1) * 34 + (face ? 33 : 0)];
+        uint32_t bits = 0;
+#pragma unroll 8
+        for (int y = 0; y < 32; ++y) bits |= (uint32_t)(Y0 + y <= h) << y;
+        sm.xh[face][z] = bits;
+    }
+    uint32_t v_or = 0, v_and = kFull, o_and = kFull;
+    v4::IdPlanes ip;
+#pragma unroll
+    for (int s = 0; s < v4::kSlabs; ++s) {
+        uint4* slab4 = reinterpret_cast<uint4*>(sm.tile.ring[s & 1]);
+#pragma unroll 2
+        for (int k = 0; k < 4; ++k) {
+            const int j = s * 1024 + tid + k * kThreads;      // uint4 index inside the chunk: (z*32 + y)*4 + piece
+            const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
+            const short* hp = s_h + (z + 1) * 34 + x0 + 1;
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
+            slab4[tid + k * kThreads] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncthreads();                              // slab s complete (and slab s-1 converted by everybody: its buffer is next)
+        v5::convert_ring_slab(sm, s, v_or, v_and, o_and, ip);
+    }
+    const v4::ChunkFlags fl = v5::reduce_flags_g(sm, v_or, v_and, o_and);   // barriers: occupancy and halo published, ring dead
+    const bool with_eq = !fl.single_id;               // terrain ids are 1..4: a chunk with several ids always takes the plane path
+    if (with_eq) v5::store_id_planes_g(sm, ip);
+    if (tid < 192) sm.rows[tid] = 0u;
+    __syncthreads();
+    const bool any = __syncthreads_or(v5::build_masks_g(sm, with_eq, with_eq) != 0);
+    if (!any) {
+        if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
+        return;
+    }
+    const short* hcol = s_h;
+    v5::emit_greedy(sm, chunk, with_eq, out, [hcol, Y0](int idx) -> uint32_t {
+        const int x = idx & 31, y = (idx >> 5) & 31, z = idx >> 10;
+        return terrain_block(hcol[(z + 1) * 34 + x + 1], Y0 + y);
+    }, prof);
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+terrain_mesh_kernel_g(const vxp_coord* __restrict__ coords, uint32_t n, ColumnScratch cs, v4::MeshOut out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    v5::SmemG& sm = *reinterpret_cast<v5::SmemG*>(smem_raw);
+    __shared__ short s_h[34 * 34];
+    __shared__ uint32_t s_item[2];
+    const uint32_t nwork = cs.count[1];
+    if (threadIdx.x == 0) s_item[0] = atomicAdd(cs.count + 2, 1u);
+    __syncthreads();
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t item = s_item[it & 1];
+        if (item >= nwork) break;
+        if (threadIdx.x == 0) s_item[(it + 1) & 1] = atomicAdd(cs.count + 2, 1u);
+        terrain_mesh_chunk_g(sm, s_h, coords, cs, cs.slot_of_chunk[n + item], out);
+        __syncthreads();
+    }
+}
+
 // ====================================================================== launchers
 
 template <class K>
@@ -274,6 +363,7 @@ cudaError_t configure_device() {
     if (e == cudaSuccess) e = set_smem(v5::mesh_kernel_g, sizeof(v5::SmemG));
     if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel<false>, sizeof(v4::Smem<false>));
     if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel<true>, sizeof(v4::Smem<true>));
+    if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel_g, sizeof(v5::SmemG));
     return e;
 }
 
@@ -472,8 +562,14 @@ cudaError_t launch_terrain_mesh(const vxp_coord* d_coords, uint32_t n, uint64_t 
     column_heights_kernel<<<hgrid, kThreads, 0, stream>>>(cs, seed);
     column_classify_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_coords, n, cs, o.meta);
     // the work list's length is only known on the device: a resident grid strides over it
-    const uint32_t mgrid = n < (uint32_t)(3 * sms) ? n : (uint32_t)(3 * sms);
-    if (greedy)
+    // generation 5 (four CTAs per SM) pays off when every CTA draws many work items: world of 274 625 chunks 881 -> 850 us,
+    // but a 4096-chunk batch (1540 work items over 592 CTAs instead of 444) 94 -> 113 us
+    const bool g5 = greedy && !greedy_v4() && (n >= 32768u || getenv("VXP_FUSED_V5") != nullptr);
+    const uint32_t per_sm = g5 ? 4u : 3u;
+    const uint32_t mgrid = n < per_sm * (uint32_t)sms ? n : per_sm * (uint32_t)sms;
+    if (g5)
+        terrain_mesh_kernel_g<<<mgrid, kThreads, sizeof(v5::SmemG), stream>>>(d_coords, n, cs, mesh_out(o));
+    else if (greedy)
         terrain_mesh_kernel<true><<<mgrid, kThreads, sizeof(v4::Smem<true>), stream>>>(d_coords, n, cs, mesh_out(o));
     else
         terrain_mesh_kernel<false><<<mgrid, kThreads, sizeof(v4::Smem<false>), stream>>>(d_coords, n, cs, mesh_out(o));
