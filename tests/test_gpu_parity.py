@@ -672,3 +672,18 @@ def test_fused_world_generation5_matches_generation4(mesher, monkeypatch):
         nbs = [O.terrain_fill(42, c[0] + d[0], c[1] + d[1], c[2] + d[2]) for d in S.DIRS]
         want = O.mesh_chunk_keys(O.terrain_fill(42, *c), nbs, 1)
         assert np.array_equal(np.sort(S.keys_from_verts(hb.chunk(int(i))[0])), want), c
+
+
+def test_greedy_staging_fallbacks(mesher):
+    """Chunks that do not fit the greedy kernel's staging area in one go: sparse layers of per-voxel random ids
+    (few non-empty plane rows, thousands of quads: staged and flushed in windows of ordinals) and dense noise
+    (the sweep log itself does not fit: stepped sweep)."""
+    rng = np.random.default_rng(21)
+    v = np.zeros((3, 32, 32, 32), dtype=np.uint16)                   # [z][y][x]
+    v[0, 2::6] = rng.integers(1, 5, (5, 32, 32))                     # five separate z-layers
+    v[1, :, 3::7, :] = rng.integers(1, 7, (32, 5, 32))               # five separate y-layers
+    v[2] = np.where(rng.random((32, 32, 32)) < 0.5, rng.integers(1, 5, (32, 32, 32)), 0)
+    vox = v.reshape(3, -1)
+    host = gpu_mesh(mesher, vox, None, 1)
+    assert host.meta[0, 1] > 7000 and host.meta[1, 1] > 7000
+    check_against_oracle(host, vox, None, 1)

@@ -414,7 +414,9 @@ struct RecStore {
     uint32_t* b;
     __device__ __forceinline__ uint32_t& at(uint32_t i) const { return i < na ? a[i] : b[i - na]; }
 };
-__device__ __forceinline__ void stage_births_g(const SmemG& sm, bool with_eq, const SweepLog& log, uint32_t nL, const RecStore& rec) {
+// Only the records with ordinals in [lo, hi) are staged, at ordinal - lo.
+__device__ __forceinline__ void stage_births_g(const SmemG& sm, bool with_eq, const SweepLog& log, uint32_t nL, const RecStore& rec,
+                                               uint32_t lo = 0u, uint32_t hi = 0xFFFFFFFFu) {
     for (uint32_t i = threadIdx.x; i < nL; i += kThreads) {
         const uint2 en = log.entry[i];
         const uint32_t plane = (en.y >> 5) & 255u, v = en.y & 31u;
@@ -423,12 +425,14 @@ __device__ __forceinline__ void stage_births_g(const SmemG& sm, bool with_eq, co
         const uint32_t Hv = plane_h_row_g(sm, with_eq, plane, v);
         uint32_t NS = R & ~((R << 1) & Hv), NE = R & ~((R >> 1) & (Hv >> 1));
         uint32_t pos = log.first[plane] + (en.y >> 13);
+        if (pos >= hi || pos + __popc(NS) <= lo) continue;
         const uint32_t base = (en.y & 0x1FFFu) << 5;
         do {
             const uint32_t u = __ffs(NS) - 1, e = __ffs(NE) - 1;
             NS &= NS - 1;
             NE &= NE - 1;
-            rec.at(pos++) = base | u | (e - u) << 18;
+            if (pos >= lo && pos < hi) rec.at(pos - lo) = base | u | (e - u) << 18;
+            ++pos;
         } while (NS);
     }
 }
@@ -479,6 +483,25 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
             prof.mark(6);
             flush_staging(sm, [rec, &log](uint32_t i) { const uint32_t r = rec.at(i); return r | (run_height(log, r) - 1u) << 23; },
                           Q, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, mi, Q, f, out); }, true);
+            prof.mark(7);
+            return;
+        }
+        // More records than fit at once, but the log is there: stage and flush them in windows of ordinals (no second sweep).
+        const uint32_t window = 3u * kPlaneWords + kCap - 2 * nL;     // rec is the split store
+        if (window >= 1024u) {
+            prof.count(14);
+            for (uint32_t lo = 0; lo < Q; lo += window) {
+                const uint32_t hi = min(Q, lo + window);
+                __syncthreads();                      // first round: first_run published, sweep over; later: previous flush done
+                stage_births_g(sm, with_eq, log, nL, rec, lo, hi);
+                __syncthreads();
+                bool ok;
+                if (lo == 0) ok = flush_staging(sm, [rec, &log](uint32_t i) { const uint32_t r = rec.at(i); return r | (run_height(log, r) - 1u) << 23; },
+                                                hi, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, mi, Q, f, out); }, true);
+                else ok = flush_staging(sm, [rec, &log](uint32_t i) { const uint32_t r = rec.at(i); return r | (run_height(log, r) - 1u) << 23; },
+                                        hi - lo, lo, out, id_of, nothing, false);
+                if (!ok) return;
+            }
             prof.mark(7);
             return;
         }
