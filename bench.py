@@ -513,6 +513,15 @@ def main():
                                   "unpack_raw_gbs": n_step * CHUNK_BYTES / (ms_unpack * 1e-3) / 1e9}
             m._lib.vxp_host_free(pp)
             m._lib.vxp_host_free(op)
+            # level of detail: the 16^3 block of chunks -> 8^3 half-resolution chunks (reads 8 bytes per byte written)
+            k8 = np.array([[(2 * X + (c & 1)) + 16 * ((2 * Y + ((c >> 1) & 1)) + 16 * (2 * Z + (c >> 2))) for c in range(8)]
+                           for Z in range(8) for Y in range(8) for X in range(8)], dtype=np.int32)
+            dk8 = torch.from_numpy(k8).to(dev)
+            lod_out = torch.empty((512, 32768), dtype=torch.int16, device=dev)
+            ms_lod = timed(lambda s: m.downsample(batches[s % len(batches)], dk8, out=lod_out), steps=40)
+            also["lod_downsample"] = {"ms_per_step": ms_lod, "chunks_in": n_step, "chunks_out": 512,
+                                      "hbm_gbs": (n_step + 512) * CHUNK_BYTES / (ms_lod * 1e-3) / 1e9,
+                                      "frac": (n_step + 512) * CHUNK_BYTES / (ms_lod * 1e-3) / 1e9 / peak}
             # latency of one voxel edit -> re-meshed chunks, device level (no host round trip inside;
             # timed with events over back-to-back calls) and host level (edits up, new meshes down, wall clock)
             from voxelphile_b200 import EDIT_DTYPE

@@ -156,6 +156,14 @@ vxp_status vxp_pack_chunks(vxp_ctx *ctx, const uint16_t *d_voxels, uint32_t n, u
 vxp_status vxp_unpack_chunks(vxp_ctx *ctx, const uint8_t *d_packed, const uint64_t *d_offsets, uint32_t n,
                              uint16_t *d_voxels);
 
+/* ---- level of detail (SPEC §11) ------------------------ */
+/* d_out[i] = the 2 x 2 x 2 stored chunks d_child8[i][dx + 2*dy + 4*dz] (indices into d_voxels, -1 = air) at half
+ * resolution: output voxel (x,y,z) is the first non-air voxel of its 2 x 2 x 2 block in the order y high, z low,
+ * x low, air if there is none.  The result is an ordinary chunk: mesh it with vxp_mesh_batch, apply the call
+ * again for the next level.  d_out must not overlap the chunks it reads. */
+vxp_status vxp_downsample_chunks(vxp_ctx *ctx, const uint16_t *d_voxels, const int32_t *d_child8, uint32_t n_out,
+                                 uint16_t *d_out);
+
 /* ---- host level: host pointers in, context-owned pinned results out ---- */
 vxp_status vxp_terrain_fill_host(vxp_ctx *ctx, const vxp_coord *coords, uint32_t n,
                                  uint64_t seed, uint16_t *voxels);

@@ -104,6 +104,9 @@ extern "C" {
     pub fn vxp_unpack_chunks(ctx: *mut vxp_ctx, d_packed: *const u8, d_offsets: *const u64, n: u32,
                              d_voxels: *mut u16) -> vxp_status;
 
+    pub fn vxp_downsample_chunks(ctx: *mut vxp_ctx, d_voxels: *const u16, d_child8: *const i32, n_out: u32,
+                                 d_out: *mut u16) -> vxp_status;
+
     pub fn vxp_terrain_fill_host(ctx: *mut vxp_ctx, coords: *const vxp_coord, n: u32, seed: u64,
                                  voxels: *mut u16) -> vxp_status;
     pub fn vxp_mesh_chunks_host(ctx: *mut vxp_ctx, voxels: *const u16, nbr6: *const i32, n: u32,

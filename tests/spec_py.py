@@ -286,3 +286,19 @@ def unpack_record(rec: bytes) -> np.ndarray:
 
 def record_size(rec_head: bytes) -> int:
     return 48 + int(np.frombuffer(rec_head[8:12], dtype="<u4")[0])
+
+
+# --------------------------------------------------------------------------- SPEC §11 level of detail
+def downsample(children) -> np.ndarray:
+    """children: list of 8 arrays [32768] or None, index dx + 2 dy + 4 dz -> one chunk [32768]."""
+    region = np.zeros((64, 64, 64), dtype=np.uint16)              # [z][y][x]
+    for c, v in enumerate(children):
+        if v is None:
+            continue
+        dx, dy, dz = c & 1, (c >> 1) & 1, c >> 2
+        region[32 * dz:32 * dz + 32, 32 * dy:32 * dy + 32, 32 * dx:32 * dx + 32] = np.asarray(v, np.uint16).reshape(32, 32, 32)
+    out = np.zeros((32, 32, 32), dtype=np.uint16)
+    for j, k, i in ((1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1), (0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1)):   # (y, z, x) offsets
+        cand = region[k::2, j::2, i::2]
+        out = np.where(out == 0, cand, out)
+    return out.reshape(-1)

@@ -687,3 +687,44 @@ def test_greedy_staging_fallbacks(mesher):
     host = gpu_mesh(mesher, vox, None, 1)
     assert host.meta[0, 1] > 7000 and host.meta[1, 1] > 7000
     check_against_oracle(host, vox, None, 1)
+
+
+# --------------------------------------------------------------------------- SPEC §11: level of detail
+def test_downsample_and_mesh_lod(mesher):
+    """vxp_downsample_chunks against the numpy restatement (random chunks, missing children, terrain), and the
+    downsampled terrain meshed by the ordinary kernels against the oracle mesh of the restated LOD chunks."""
+    import torch
+    from voxelphile_b200 import grid_coords, neighbour_table
+    rng = np.random.default_rng(9)
+    vox = np.where(rng.random((20, 32768)) < 0.4, rng.integers(1, 400, (20, 32768)), 0).astype(np.uint16)
+    child = rng.integers(-1, 20, size=(6, 8)).astype(np.int32)
+    child[0] = -1
+    got = mesher.downsample(dev(vox.view(np.int16)), dev(child))
+    torch.cuda.synchronize()
+    got = got.cpu().numpy().view(np.uint16)
+    for i in range(6):
+        want = S.downsample([None if c < 0 else vox[c] for c in child[i]])
+        assert np.array_equal(got[i], want), i
+    # two levels of a terrain block: 8x8x8 chunks -> 4x4x4 -> 2x2x2, each level meshed greedy
+    coords = grid_coords((0, 4, 0), (8, 12, 8))
+    level = O.terrain_fill_batch(42, coords)
+    dlevel = dev(level.view(np.int16))
+    dim = 8
+    while dim > 2:
+        half = dim // 2
+        idx = lambda x, y, z, d=dim: x + d * (y + d * z)             # grid_coords order: x fastest
+        assert tuple(coords[idx(1, 0, 0)] - coords[0]) == (1, 0, 0) or dim != 8
+        kids = np.array([[idx(2 * X + (c & 1), 2 * Y + ((c >> 1) & 1), 2 * Z + (c >> 2)) for c in range(8)]
+                         for Z in range(half) for Y in range(half) for X in range(half)], dtype=np.int32)
+        want = np.stack([S.downsample([level[c] for c in row]) for row in kids])
+        dlevel = mesher.downsample(dlevel, dev(kids))
+        torch.cuda.synchronize()
+        assert np.array_equal(dlevel.cpu().numpy().view(np.uint16), want), dim
+        lod_coords = grid_coords((0, 0, 0), (half, half, half))
+        nbr = neighbour_table(lod_coords)
+        out = mesher.mesh(dlevel, dev(nbr), 1, capacity=half ** 3 * 8192)
+        torch.cuda.synchronize()
+        want_hash, want_cnt = O.mesh_batch_hash(want, nbr, 1)
+        host = out.to_host()
+        assert np.array_equal(host.meta[:, 1], want_cnt) and np.array_equal(_chunk_hashes(host), want_hash), dim
+        level, dim = want, half

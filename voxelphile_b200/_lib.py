@@ -65,6 +65,7 @@ SIGNATURES = {
     "vxp_unpack_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "vxp_mesh_packed_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                              C.c_int, C.POINTER(MeshHost)]),
+    "vxp_downsample_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "vxp_terrain_fill_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]),
     "vxp_mesh_chunks_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                              C.POINTER(MeshHost)]),

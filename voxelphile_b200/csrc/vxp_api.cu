@@ -611,6 +611,17 @@ vxp_status vxp_unpack_chunks(vxp_ctx* ctx, const uint8_t* d_packed, const uint64
     return VXP_OK;
 }
 
+// ------------------------------------------------------------------ level of detail (SPEC §11)
+
+vxp_status vxp_downsample_chunks(vxp_ctx* ctx, const uint16_t* d_voxels, const int32_t* d_child8, uint32_t n_out, uint16_t* d_out) {
+    if (!ctx || (n_out && (!d_voxels || !aligned16(d_voxels) || !d_child8 || !d_out || !aligned16(d_out)))) return VXP_ERR_BAD_ARG;
+    DeviceGuard g(ctx->device);
+    ctx->chain_open = false;
+    VXP_CUDA(ctx, vxp::launch_downsample_chunks(d_voxels, d_child8, n_out, d_out, ctx->stream));
+    ctx->launches += n_out ? 1 : 0;
+    return VXP_OK;
+}
+
 // ------------------------------------------------------------------ host level
 
 vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t n, uint64_t seed,

@@ -186,3 +186,57 @@ cudaError_t launch_unpack_chunks(const unsigned char* d_packed, const unsigned l
 }
 
 }  // namespace vxp
+
+// ====================================================================== LOD (SPEC §11)
+// One output chunk = 2 x 2 x 2 stored chunks at half resolution.  One CTA per output chunk; a thread produces 8
+// output voxels (one 16-byte store) from 4 rows x 16 input voxels.  HBM-bound: 8 bytes read per byte written.
+namespace vxp {
+namespace {
+// first non-air of (a, b) per u16 lane pair -> one u16: a if a != 0 else b
+__device__ __forceinline__ uint32_t first_solid(uint32_t a, uint32_t b) { return a ? a : b; }
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads) downsample_chunks_kernel(const uint16_t* __restrict__ voxels,
+                                                                      const int32_t* __restrict__ child8, uint32_t n_out,
+                                                                      uint16_t* __restrict__ out) {
+    const uint32_t oc = blockIdx.x;
+    if (oc >= n_out) return;
+    __shared__ int s_child[8];
+    if (threadIdx.x < 8) s_child[threadIdx.x] = child8[8 * (size_t)oc + threadIdx.x];
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)oc * VXP_CHUNK_VOXELS);
+    for (int j = threadIdx.x; j < 4096; j += kThreads) {          // j = (z*32 + y)*4 + p
+        const int z = j >> 7, y = (j >> 2) & 31, p = j & 3;        // output voxels x = 8p .. 8p+7
+        const int c = (p >> 1) | (y >> 4) << 1 | (z >> 4) << 2;    // child: dx + 2 dy + 4 dz
+        const int ch = s_child[c];
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (ch >= 0) {
+            const uint16_t* src = voxels + (size_t)ch * VXP_CHUNK_VOXELS;
+            const int xi = (16 * p) & 31, yi = (2 * y) & 31, zi = (2 * z) & 31;
+            uint32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            // priority: y high first, then z low, then x low (SPEC §11)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int yy = yi + 1 - (t >> 1), zz = zi + (t & 1);
+                const uint4* row = reinterpret_cast<const uint4*>(src + xi + 32 * yy + 1024 * zz);
+                const uint4 a = __ldg(row), b = __ldg(row + 1);    // 16 input voxels
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {                      // input voxels 2e (low half), 2e+1 (high half) -> output voxel e
+                    const uint32_t v = first_solid(w[e] & 0xFFFFu, w[e] >> 16);
+                    o[e] = first_solid(o[e], v);
+                }
+            }
+            r = make_uint4(o[0] | o[1] << 16, o[2] | o[3] << 16, o[4] | o[5] << 16, o[6] | o[7] << 16);
+        }
+        dst[j] = r;
+    }
+}
+
+cudaError_t launch_downsample_chunks(const uint16_t* d_voxels, const int32_t* d_child8, uint32_t n_out, uint16_t* d_out,
+                                     cudaStream_t stream) {
+    if (n_out == 0) return cudaSuccess;
+    downsample_chunks_kernel<<<n_out, kThreads, 0, stream>>>(d_voxels, d_child8, n_out, d_out);
+    return cudaGetLastError();
+}
+}  // namespace vxp

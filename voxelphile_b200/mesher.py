@@ -308,6 +308,17 @@ class Mesher:
                                                    C.byref(h)))
         return self._host_result(h, n, copy=False)
 
+    # ------------------------------------------------------------ level of detail (SPEC §11)
+    def downsample(self, voxels: "torch.Tensor", child8: "torch.Tensor", out: Optional["torch.Tensor"] = None) -> "torch.Tensor":
+        """vxp_downsample_chunks: child8 int32 [n_out, 8] (dx + 2 dy + 4 dz, -1 = air) -> int16 [n_out, 32768]."""
+        import torch
+        n_out = int(child8.shape[0])
+        assert child8.is_cuda and child8.is_contiguous() and child8.shape[1] == 8
+        if out is None:
+            out = torch.empty((n_out, CHUNK_VOXELS), dtype=torch.int16, device=voxels.device)
+        self._check(self._lib.vxp_downsample_chunks(self._h, voxels.data_ptr(), child8.data_ptr(), n_out, out.data_ptr()))
+        return out
+
     # ------------------------------------------------------------ host level (numpy in, numpy out)
     def _host_result(self, h: _lib.MeshHost, n: int, copy: bool) -> HostMesh:
         q = int(h.total_quads)
