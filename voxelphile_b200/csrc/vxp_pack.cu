@@ -111,11 +111,15 @@ __global__ void __launch_bounds__(kThreads) pack_chunks_kernel(const uint16_t* _
         uint32_t out = 0;
         // chunks are mostly runs of one id: look an id up only when it differs from the previous voxel's
         uint32_t lastv = w[0] & 0xFFFFu, lasti = palette_index(sh.palette, len, lastv);
+        if (q.x == q.y && q.x == q.z && q.x == q.w && lastv == (q.x >> 16)) {   // eight equal voxels: one look-up, one multiply
+            out = lasti * (bits == 1u ? 0xFFu : bits == 2u ? 0x5555u : 0x11111111u);
+        } else {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const uint32_t v = (t & 1) ? w[t >> 1] >> 16 : w[t >> 1] & 0xFFFFu;
-            if (v != lastv) { lastv = v; lasti = palette_index(sh.palette, len, v); }
-            out |= lasti << (bits * t);
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t v = (t & 1) ? w[t >> 1] >> 16 : w[t >> 1] & 0xFFFFu;
+                if (v != lastv) { lastv = v; lasti = palette_index(sh.palette, len, v); }
+                out |= lasti << (bits * t);
+            }
         }
         if (bits == 1u) data[j] = (unsigned char)out;
         else if (bits == 2u) reinterpret_cast<unsigned short*>(data)[j] = (unsigned short)out;
@@ -155,17 +159,29 @@ __global__ void __launch_bounds__(kThreads) unpack_chunks_kernel(const unsigned 
         for (int k = 0; k < 16; ++k) dst[tid + k * kThreads] = make_uint4(bb, bb, bb, bb);
         return;
     }
-    for (int k = 0; k < 16; ++k) {
-        const int j = tid + k * kThreads;
-        if (bits == 16u) { dst[j] = __ldg(reinterpret_cast<const uint4*>(data) + j); continue; }
-        const uint32_t in = bits == 1u ? data[j] : bits == 2u ? reinterpret_cast<const unsigned short*>(data)[j]
-                                                             : reinterpret_cast<const uint32_t*>(data)[j];
-        const uint32_t mask = (1u << bits) - 1u;
-        uint32_t w[4];
+    if (bits == 16u) {
+#pragma unroll 8
+        for (int k = 0; k < 16; ++k) dst[tid + k * kThreads] = __ldg(reinterpret_cast<const uint4*>(data) + tid + k * kThreads);
+        return;
+    }
+    const uint32_t mask = (1u << bits) - 1u;
+#pragma unroll 1
+    for (int k0 = 0; k0 < 16; k0 += 8) {                  // eight loads in flight per thread, then eight stores
+        uint32_t in[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            w[e] = s_pal[(in >> (bits * (2 * e))) & mask] | s_pal[(in >> (bits * (2 * e + 1))) & mask] << 16;
-        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int k = 0; k < 8; ++k) {
+            const int j = tid + (k0 + k) * kThreads;
+            in[k] = bits == 1u ? data[j] : bits == 2u ? reinterpret_cast<const unsigned short*>(data)[j]
+                                                      : reinterpret_cast<const uint32_t*>(data)[j];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                w[e] = s_pal[(in[k] >> (bits * (2 * e))) & mask] | s_pal[(in[k] >> (bits * (2 * e + 1))) & mask] << 16;
+            dst[tid + (k0 + k) * kThreads] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 
