@@ -448,9 +448,18 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
     if (tid == 0) sm.cursor = 0;
     SweepG st;
     sweep_init_g(st, sm, with_eq);
+    const int lane = tid & 31, warp = tid >> 5;
     const uint32_t rm = tid < 192 ? sm.rows[tid] : 0u;   // from build_masks_g
-    uint32_t nL;
-    const uint32_t seg = block_excl_scan((uint32_t)__popc(rm), sm.scratch, &nL);   // barriers: cursor = 0 published
+    // first log entry of every plane = exclusive prefix of the planes' non-empty rows.  Every warp adds up the six
+    // faces for itself (six loads, six warp reductions): no barrier, where a block-wide scan needs two.
+    uint32_t nL = 0, seg = 0;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const uint32_t tot = __reduce_add_sync(kFull, (uint32_t)__popc(sm.rows[f * 32 + lane]));
+        nL += tot;
+        if (f < warp) seg += tot;
+    }
+    seg += warp_incl_scan((uint32_t)__popc(rm), lane) - (uint32_t)__popc(rm);
     if (tid < 192) sm.seg[tid] = seg;
     const bool log_fits = 2 * nL <= kCap;
     SweepLog log;
@@ -463,7 +472,18 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
     if (log_fits) {
         uint32_t births = 0;
         if (tid < 192) births = sweep_log_g(st, rm, (uint32_t)tid, log.entry + seg);
-        const uint32_t first_run = block_excl_scan(births, sm.scratch, &Q);          // barriers: log published
+        // ordinal of every plane's first run: block-wide exclusive scan of the births, with one barrier (the log
+        // is published by it too; sm.scratch is not written again before the chunk ends)
+        const uint32_t incl = warp_incl_scan(births, lane);
+        if (lane == 31) sm.scratch[warp] = incl;
+        __syncthreads();
+        uint32_t first_run = incl - births;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t t = sm.scratch[w];
+            if (w < warp) first_run += t;
+            Q += t;
+        }
         if (tid < 192) sm.first_run[tid] = first_run;
         if (tid == 0) f = reserve_quads(sm, out, Q);
         prof.mark(5);
@@ -506,6 +526,7 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
             return;
         }
     } else {
+        __syncthreads();                              // cursor = 0 published
         if (tid < 192) {
 #pragma unroll 1
             for (int v = 0; v <= 32; ++v) sweep_step_g(st, v, staging, 0u, &sm.cursor);
