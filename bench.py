@@ -461,6 +461,15 @@ def main():
             also["terrain_fill"] = {"chunks_per_s": n_step / (ms * 1e-3), "ms_per_step": ms,
                                     "hbm_gbs": n_step * CHUNK_BYTES / (ms * 1e-3) / 1e9,
                                     "frac": n_step * CHUNK_BYTES / (ms * 1e-3) / 1e9 / peak}
+            # a world-sized batch (32^3 chunks, 2 GiB of voxels): the chunks of a column share its heights
+            from voxelphile_b200 import grid_coords
+            big_c = torch.from_numpy(grid_coords((0, 0, 0), (32, 32, 32))).to(dev)
+            big_v = torch.empty((32768, 32768), dtype=torch.int16, device=dev)
+            ms = timed(lambda s: m.terrain_fill(big_c, 100 + s, out=big_v), steps=10)
+            also["terrain_fill_32768"] = {"chunks_per_s": 32768 / (ms * 1e-3), "ms_per_step": ms,
+                                          "hbm_gbs": 32768 * CHUNK_BYTES / (ms * 1e-3) / 1e9,
+                                          "frac": 32768 * CHUNK_BYTES / (ms * 1e-3) / 1e9 / peak}
+            del big_v
             fprobe = m.alloc_mesh(n_step, 0)
             m.terrain_mesh(dcoords, 42, GREEDY, out=fprobe)
             torch.cuda.synchronize()

@@ -728,3 +728,21 @@ def test_downsample_and_mesh_lod(mesher):
         host = out.to_host()
         assert np.array_equal(host.meta[:, 1], want_cnt) and np.array_equal(_chunk_hashes(host), want_hash), dim
         level, dim = want, half
+
+
+def test_terrain_fill_large_batches_bit_exact(mesher, monkeypatch):
+    """Large batches (>= 16 384 chunks; VXP_FILL_COLUMNS selects it for these smaller ones) take the shared-column
+    path of vxp_terrain_fill_batch: a tall block (16 chunks per column), a flat sheet (every column its own) and a
+    shuffled list with negative coordinates, against the oracle."""
+    import torch
+    from voxelphile_b200 import grid_coords
+    monkeypatch.setenv("VXP_FILL_COLUMNS", "1")
+    rng = np.random.default_rng(13)
+    tall = grid_coords((0, 0, 0), (8, 16, 8))                        # 1024 chunks, 64 columns
+    sheet = grid_coords((-20, 8, -20), (20, 9, 20))                  # 1600 chunks, 1600 columns
+    mixed = grid_coords((-6, 4, -6), (6, 13, 6))                     # 1296 chunks
+    mixed = mixed[rng.permutation(mixed.shape[0])]
+    for seed, coords in ((42, tall), (7, sheet), (2**63 + 5, mixed)):
+        got = mesher.terrain_fill(dev(coords), seed)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy().view(np.uint16), O.terrain_fill_batch(seed, coords)), seed

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -224,6 +225,11 @@ vxp_status column_scratch(vxp_ctx* ctx, uint32_t n, vxp::ColumnScratch* out) {
     *out = ctx->columns;
     return VXP_OK;
 }
+
+// terrain fill: batches of at least this many chunks go through the shared column heights.  Measured on the 16^3 block
+// (4096 chunks, 16 per column): 60.1 us direct, 65.6 us through the columns - the fill kernel itself drops to ~50 us but
+// two memsets and two small kernels in front of it cost ~15 us, which only a larger batch amortises.
+constexpr uint32_t kColumnFillMin = 16384;
 
 bool valid_mode(vxp_mode m) { return m == VXP_MODE_CULLED || m == VXP_MODE_GREEDY; }
 
@@ -467,6 +473,14 @@ vxp_status vxp_terrain_fill_batch(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
     if (!ctx || (n && (!d_coords || !d_voxels)) || !aligned16(d_voxels)) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     ctx->chain_open = false;
+    if ((n >= kColumnFillMin || getenv("VXP_FILL_COLUMNS")) && !getenv("VXP_FILL_DIRECT")) {   // large batch: the chunks of a column share its heights
+        vxp::ColumnScratch cols{};
+        const vxp_status s = column_scratch(ctx, n, &cols);
+        if (s != VXP_OK) return s;
+        VXP_CUDA(ctx, vxp::launch_terrain_fill_columns(d_coords, n, seed, d_voxels, cols, ctx->stream));
+        ctx->launches += 3;
+        return VXP_OK;
+    }
     VXP_CUDA(ctx, vxp::launch_terrain_fill(d_coords, n, seed, d_voxels, ctx->stream));
     ctx->launches += n ? 1 : 0;
     return VXP_OK;

@@ -174,6 +174,48 @@ __global__ void __launch_bounds__(kThreads) column_classify_kernel(const vxp_coo
     if (surface) cs.slot_of_chunk[n + base + __popc(m & ((1u << lane) - 1u))] = i;   // work list lives behind slot_of_chunk
 }
 
+// Terrain fill of a large batch: the chunks of a column (cx,cz) share its heights (column_insert_kernel /
+// column_heights_kernel above), so a chunk only reads its 32 x 32 heights (2 KiB, L2) and streams 64 KiB out.
+// One CTA per chunk, same store loop as terrain_fill_kernel.
+__global__ void __launch_bounds__(kThreads) terrain_fill_columns_kernel(const vxp_coord* __restrict__ coords, uint32_t n,
+                                                                         ColumnScratch cs, uint16_t* __restrict__ out) {
+    __shared__ short s_h[1024];
+    __shared__ short s_zmin[32], s_zmax[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= n) return;
+    const short* col = cs.heights + (size_t)cs.id_of_slot[cs.slot_of_chunk[chunk]] * kColStride;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int z = warp + k * kWarps;                 // a warp owns the 32 columns of one z-layer
+        const int h = col[(z + 1) * 34 + lane + 1];
+        s_h[z * 32 + lane] = (short)h;
+        const int lo = __reduce_min_sync(kFull, h), hi = __reduce_max_sync(kFull, h);
+        if (lane == 0) { s_zmin[z] = (short)lo; s_zmax[z] = (short)hi; }
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)chunk * VXP_CHUNK_VOXELS);
+    const int Y0 = 32 * coords[chunk].y;
+#pragma unroll 4
+    for (int j = tid; j < 4096; j += kThreads) {         // j = (z*32 + y)*4 + p
+        const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
+        uint4 v;
+        if (Y > s_zmax[z]) {                             // above every column of this layer: air
+            v = make_uint4(0, 0, 0, 0);
+        } else if (Y < s_zmin[z] - 3) {                  // below the dirt of every column: stone / slate by Y only
+            const uint32_t b = ((Y >> 3) & 1) ? 4u : 3u, bb = b | b << 16;
+            v = make_uint4(bb, bb, bb, bb);
+        } else {
+            const short* hp = s_h + z * 32 + x0;
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        dst[j] = v;
+    }
+}
+
 // One surface chunk: footprint -> tile in shared memory -> the meshing pipeline of vxp_mesh4.cuh.
 template <bool kGreedy>
 __device__ __forceinline__ void terrain_mesh_chunk(v4::Smem<kGreedy>& sm, short* s_h, const vxp_coord* __restrict__ coords,
@@ -371,6 +413,22 @@ cudaError_t launch_terrain_fill(const vxp_coord* d_coords, uint32_t n, uint64_t 
                                 cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     terrain_fill_kernel<<<n, kThreads, 0, stream>>>(d_coords, n, seed, d_voxels);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_terrain_fill_columns(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
+                                        const ColumnScratch& cs, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(cs.keys, 0xFF, ((size_t)cs.mask + 1) * sizeof(unsigned long long), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cs.count, 0, 3 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    column_insert_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_coords, n, cs);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t hgrid = n < (uint32_t)(4 * sms) ? n : (uint32_t)(4 * sms);
+    column_heights_kernel<<<hgrid, kThreads, 0, stream>>>(cs, seed);
+    terrain_fill_columns_kernel<<<n, kThreads, 0, stream>>>(d_coords, n, cs, d_voxels);
     return cudaGetLastError();
 }
 

@@ -38,6 +38,9 @@ size_t column_record_bytes();
 cudaError_t configure_device();
 cudaError_t launch_terrain_fill(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
                                 cudaStream_t stream);
+// Large batches: the chunks of a column (cx,cz) share one height footprint (three launches; columns: scratch for n chunks).
+cudaError_t launch_terrain_fill_columns(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
+                                        const ColumnScratch& columns, cudaStream_t stream);
 cudaError_t launch_pattern_fill(const vxp_coord* d_coords, uint32_t n, int pattern, uint16_t* d_voxels,
                                 cudaStream_t stream);
 // One whole-batch launch.  `counter` is a context-owned, zero-initialised 8-byte launch counter (vxp_mesh4.cuh,
