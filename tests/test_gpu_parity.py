@@ -746,3 +746,54 @@ def test_terrain_fill_large_batches_bit_exact(mesher, monkeypatch):
         got = mesher.terrain_fill(dev(coords), seed)
         torch.cuda.synchronize()
         assert np.array_equal(got.cpu().numpy().view(np.uint16), O.terrain_fill_batch(seed, coords)), seed
+
+
+def test_new_entry_points_reject_bad_arguments_and_accept_empty_batches(mesher):
+    """Through the raw C ABI: null pointers and empty batches for the re-mesh, wire-format and LOD calls."""
+    import ctypes as C
+    import torch
+    from voxelphile_b200 import _lib as L
+    lib, h = mesher._lib, mesher._h
+    BAD, OK = L.VXP_ERR_BAD_ARG, L.VXP_OK
+    vox = torch.zeros((2, 32768), dtype=torch.int16, device="cuda")
+    out = mesher.alloc_mesh(2, 1024)
+    s = mesher._mesh_struct(out)
+    lst = torch.zeros(2, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    # vxp_mesh_list
+    assert lib.vxp_mesh_list(h, vox.data_ptr(), None, 2, None, 2, 1, C.byref(s)) == BAD
+    assert lib.vxp_mesh_list(h, None, None, 2, lst.data_ptr(), 2, 1, C.byref(s)) == BAD
+    assert lib.vxp_mesh_list(h, vox.data_ptr(), None, 2, lst.data_ptr(), 2, 9, C.byref(s)) == BAD
+    assert lib.vxp_mesh_list(h, vox.data_ptr(), None, 2, lst.data_ptr(), 0, 1, C.byref(s)) == OK
+    # vxp_remesh_edits
+    ed = torch.zeros((1, 3), dtype=torch.int32, device="cuda")
+    assert lib.vxp_remesh_edits(h, vox.data_ptr(), None, 2, ed.data_ptr(), 1, 1, lst.data_ptr(), None, C.byref(s)) == BAD
+    assert lib.vxp_remesh_edits(h, vox.data_ptr(), None, 2, None, 1, 1, lst.data_ptr(), cnt.data_ptr(), C.byref(s)) == BAD
+    assert lib.vxp_remesh_edits(h, vox.data_ptr(), None, 2, ed.data_ptr(), 0, 1, lst.data_ptr(), cnt.data_ptr(), C.byref(s)) == OK
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == 0 and int(out.total.item()) == 0
+    # out-of-range edits are ignored, in-range ones applied
+    e2 = np.array([(5, 0, 0, 0, 9), (1, 40, 0, 0, 9), (1, 3, 4, 5, 9)], dtype=EDIT_DTYPE)
+    d, c, o = mesher.remesh_edits(vox, None, dev(e2.view(np.int32).reshape(-1, 3)), 1)
+    torch.cuda.synchronize()
+    assert int(c.item()) == 1 and int(d[0].item()) == 1 and int(vox[1, 3 + 32 * 4 + 1024 * 5].item()) == 9
+    assert int(o.total.item()) == 6
+    # vxp_pack_chunks / vxp_unpack_chunks / vxp_downsample_chunks
+    tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+    off = torch.zeros(2, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(1 << 18, dtype=torch.uint8, device="cuda")
+    assert lib.vxp_pack_chunks(h, vox.data_ptr(), 2, buf.data_ptr(), 1 << 18, off.data_ptr(), None) == BAD
+    assert lib.vxp_pack_chunks(h, None, 2, buf.data_ptr(), 1 << 18, off.data_ptr(), tot.data_ptr()) == BAD
+    assert lib.vxp_pack_chunks(h, vox.data_ptr(), 2, buf.data_ptr() + 8, 1 << 17, off.data_ptr(), tot.data_ptr()) == BAD
+    assert lib.vxp_pack_chunks(h, vox.data_ptr(), 0, None, 0, None, tot.data_ptr()) == OK
+    assert lib.vxp_unpack_chunks(h, None, off.data_ptr(), 2, vox.data_ptr()) == BAD
+    assert lib.vxp_unpack_chunks(h, buf.data_ptr(), off.data_ptr(), 0, None) == OK
+    kids = torch.full((1, 8), -1, dtype=torch.int32, device="cuda")
+    assert lib.vxp_downsample_chunks(h, vox.data_ptr(), None, 1, vox.data_ptr()) == BAD
+    assert lib.vxp_downsample_chunks(h, vox.data_ptr(), kids.data_ptr(), 0, None) == OK
+    lod = mesher.downsample(vox, kids)
+    torch.cuda.synchronize()
+    assert int(lod.abs().sum().item()) == 0                       # eight missing children: air
+    mesher.synchronize()
+    # overlap switch is a plain flag
+    assert lib.vxp_ctx_set_overlap(None, 1) == BAD and lib.vxp_ctx_set_overlap(h, 1) == OK and lib.vxp_ctx_set_overlap(h, 0) == OK
