@@ -438,6 +438,14 @@ def test_overlapped_launches(mode, mname):
                 order = np.argsort(h.meta[:, 0][cnt > 0])
                 f, c = h.meta[:, 0][cnt > 0][order].astype(np.int64), cnt[cnt > 0][order].astype(np.int64)
                 assert f[0] == 0 and np.array_equal(f[1:], np.cumsum(c)[:-1]), "ranges must tile [0, Q)"
+        # a long stream (what bench.py does): the last two results are still exact
+        for k in range(400):
+            m.mesh(batches[k % 4], dn, mode, out=outs[k % 2])
+        torch.cuda.synchronize()
+        for k in (398, 399):
+            h = outs[k % 2].to_host()
+            tq, cnt, hs = serial[k % 4]
+            assert h.total_quads == tq and np.array_equal(h.meta[:, 1], cnt) and np.array_equal(_chunk_hashes(h), hs), k
         # modes and other calls may be mixed freely: a fill between two calls serialises them
         other = 1 - mode
         o1 = m.mesh(batches[1], dn, other, out=outs[0])

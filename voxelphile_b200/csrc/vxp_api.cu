@@ -824,6 +824,7 @@ vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t pa
     if ((s = grow_device(ctx, &ctx->d_packed, &ctx->packed_cap, (size_t)packed_bytes + 16, 1)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_offsets, &ctx->offsets_cap, n_stored, 1)) != VXP_OK) return s;
     if ((s = join_chain(ctx)) != VXP_OK) return s;
+    if (ctx->status_pending && (s = vxp_ctx_synchronize(ctx)) != VXP_OK) return s;   // an earlier vxp_unpack_chunks verdict is not lost
     ctx->world_n = n;
     ctx->world_stored = n_stored;
     ctx->world_has_nbr = nbr6 != nullptr;

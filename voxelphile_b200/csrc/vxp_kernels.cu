@@ -492,11 +492,13 @@ cudaError_t launch_mesh(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_
     // config 2 / 3 (256 runs): identity 75.7 / 82.4 us, 17 -> 69.5 / 75.4, 5 -> 70.4 / 75.7, 33 -> 70.7 / 76.0,
     // 97 -> 72.3 / 77.0, 159 (0.618 R) -> 71.9 / 76.6: small strides keep +-Y / +-Z neighbours close enough in
     // time for their halo rows to hit L2.
+    // (the two environment variables are for tuning runs only and are read once)
+    static const bool no_deal = getenv("VXP_NO_DEAL") != nullptr;
+    static const uint32_t stride_override = getenv("VXP_DEAL_STRIDE") ? (uint32_t)atoi(getenv("VXP_DEAL_STRIDE")) | 1u : 0u;
     uint32_t runs = n >> 4, stride = 0;
-    if (runs > 34 && !getenv("VXP_NO_DEAL")) {
+    if (runs > 34 && !no_deal) {
         auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
-        stride = 17u;
-        if (const char* ev = getenv("VXP_DEAL_STRIDE")) stride = ((uint32_t)atoi(ev) | 1u) % runs;   // tuning experiments only
+        stride = stride_override ? stride_override % runs : 17u;
         while (gcd(stride, runs) != 1u) stride += 2u;
     } else {
         runs = 0;
