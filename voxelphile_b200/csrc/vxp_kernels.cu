@@ -403,6 +403,7 @@ cudaError_t configure_device() {
     cudaError_t e = set_smem(v4::mesh_kernel<false>, sizeof(v4::Smem<false>));
     if (e == cudaSuccess) e = set_smem(v4::mesh_kernel<true>, sizeof(v4::Smem<true>));
     if (e == cudaSuccess) e = set_smem(v5::mesh_kernel_g, sizeof(v5::SmemG));
+    if (e == cudaSuccess) e = set_smem(v5::mesh_kernel_c, sizeof(v5::SmemC));
     if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel<false>, sizeof(v4::Smem<false>));
     if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel<true>, sizeof(v4::Smem<true>));
     if (e == cudaSuccess) e = set_smem(terrain_mesh_kernel_g, sizeof(v5::SmemG));
@@ -449,6 +450,10 @@ static bool greedy_v4() {
     static const bool v = getenv("VXP_GREEDY_V4") != nullptr;
     return v;
 }
+static bool culled_v4() {
+    static const bool v = getenv("VXP_CULLED_V4") != nullptr;
+    return v;
+}
 template <bool kGreedy>
 static cudaError_t launch_mesh_kernel(uint32_t grid, int overlap, cudaStream_t stream, const uint16_t* d_voxels,
                                       const int32_t* d_nbr6, uint32_t n, uint32_t lo, uint32_t hi, v4::MeshOut out, v4::Bnd bnd,
@@ -456,8 +461,8 @@ static cudaError_t launch_mesh_kernel(uint32_t grid, int overlap, cudaStream_t s
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    const bool g5 = kGreedy && !greedy_v4();
-    cfg.dynamicSmemBytes = g5 ? sizeof(v5::SmemG) : sizeof(v4::Smem<kGreedy>);
+    const bool g5 = kGreedy && !greedy_v4(), c5 = !kGreedy && !culled_v4();
+    cfg.dynamicSmemBytes = g5 ? sizeof(v5::SmemG) : c5 ? sizeof(v5::SmemC) : sizeof(v4::Smem<kGreedy>);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -465,6 +470,7 @@ static cudaError_t launch_mesh_kernel(uint32_t grid, int overlap, cudaStream_t s
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
     if (g5) return cudaLaunchKernelEx(&cfg, v5::mesh_kernel_g, d_voxels, d_nbr6, n, lo, hi, out, bnd, chain);
+    if (c5) return cudaLaunchKernelEx(&cfg, v5::mesh_kernel_c, d_voxels, d_nbr6, n, lo, hi, out, bnd, chain);
     return cudaLaunchKernelEx(&cfg, v4::mesh_kernel<kGreedy>, d_voxels, d_nbr6, n, lo, hi, out, bnd, chain);
 }
 
@@ -574,10 +580,10 @@ extern "C" int vxp_debug_occupancy(int greedy, int fused) {
                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, terrain_mesh_kernel<false>, kThreads, sizeof(v4::Smem<false>));
     else
         e = greedy ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v5::mesh_kernel_g, kThreads, sizeof(v5::SmemG))
-                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v4::mesh_kernel<false>, kThreads, sizeof(v4::Smem<false>));
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v5::mesh_kernel_c, kThreads, sizeof(v5::SmemC));
     return e == cudaSuccess ? n : -1;
 }
-extern "C" int vxp_debug_smem_bytes(int greedy) { return greedy ? (int)sizeof(v5::SmemG) : (int)sizeof(v4::Smem<false>); }
+extern "C" int vxp_debug_smem_bytes(int greedy) { return greedy ? (int)sizeof(v5::SmemG) : (int)sizeof(v5::SmemC); }
 
 #ifdef VXP_PROFILE
 extern "C" int vxp_debug_read_prof_time(unsigned long long* out, int max_ctas) {

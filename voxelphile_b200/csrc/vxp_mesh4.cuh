@@ -861,8 +861,8 @@ __device__ __forceinline__ void publish_range(SM& sm, uint32_t chunk, uint32_t Q
 // is in flight.  culled_emit: one packed block scan gives every thread its first ordinal and its slot in
 // the word list; the non-empty words are listed with the ordinal of their first quad; the threads share the
 // list evenly when they stage the quad records.
-template <bool kGreedy>
-__device__ __forceinline__ bool row_words_yz(const Smem<kGreedy>& sm, int y, int z, uint32_t (&wd)[6]) {
+template <class SM>
+__device__ __forceinline__ bool row_words_yz(const SM& sm, int y, int z, uint32_t (&wd)[6]) {
     const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
     const uint32_t c = o[0];
     if (c == 0) return false;
@@ -872,16 +872,16 @@ __device__ __forceinline__ bool row_words_yz(const Smem<kGreedy>& sm, int y, int
     wd[5] = c & ~o[+34];
     return true;
 }
-template <bool kGreedy>
-__device__ __forceinline__ bool row_words_x(const Smem<kGreedy>& sm, int y, int z, uint32_t (&wd)[6]) {
+template <class SM>
+__device__ __forceinline__ bool row_words_x(const SM& sm, int y, int z, uint32_t (&wd)[6]) {
     const uint32_t c = sm.occ[(z + 1) * 34 + (y + 1)];
     if (c == 0) return false;
     wd[0] = c & ~((c << 1) | ((sm.xh[0][z] >> y) & 1u));
     wd[1] = c & ~((c >> 1) | ((sm.xh[1][z] >> y) & 1u) << 31);
     return true;
 }
-template <bool kX, bool kGreedy>
-__device__ __forceinline__ uint32_t culled_count(const Smem<kGreedy>& sm) {
+template <bool kX, class SM>
+__device__ __forceinline__ uint32_t culled_count(const SM& sm) {
     const int y = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t packed = 0;
 #pragma unroll

@@ -670,5 +670,258 @@ mesh_kernel_g(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
     }
 }
 
+// ====================================================================== culled meshing, streamed: five CTAs per SM
+// The culled kernel never needed the ids of the tile either (block ids are gathered from the chunk in L2 when the
+// quads are written), so it streams the chunk through the same two-slab ring and keeps only the occupancy.  What
+// replaces generation 4's 48 KiB face-word list is a window of 2048 words (a terrain surface chunk has ~1500 non-
+// empty face words; a chunk with more is listed and flushed window by window) next to the 4096-record staging area:
+// 32 KiB in the ring + occupancy = 37.6 KiB per CTA.
+struct PostC {
+    static constexpr int kWordCap = 2048;
+    static constexpr int kCap = (2 * kSlabBytes - kWordCap * 8) / 4;   // 4096 staged quad records
+    uint2 words[kWordCap];       // .x = f<<10 | y<<5 | z | (ordinal of the word's first quad) << 13, .y = bits over x
+    uint32_t staging[kCap];
+};
+struct __align__(128) SmemC {
+    union {
+        unsigned char ring[2][kSlabBytes];
+        PostC post;
+    } tile;
+    uint32_t occ[34 * 34];
+    uint32_t xh[2][32];
+    uint32_t scratch[kWarps + 1];
+    uint32_t cursor;
+    uint32_t counted;
+    unsigned long long first;
+    unsigned long long mbar[2];
+};
+static_assert(sizeof(PostC) <= 2 * kSlabBytes, "post layout overflows the ring");
+static_assert(5 * (sizeof(SmemC) + 1024) <= 227 * 1024 + 1024, "five CTAs per SM need <= 45 KiB each");
+
+__device__ __forceinline__ void issue_ring_slab_c(SmemC& sm, const uint16_t* gvox, int s) {
+    mbar_expect_tx(&sm.mbar[s & 1], kSlabBytes);
+    tma_load_1d(sm.tile.ring[s & 1], reinterpret_cast<const unsigned char*>(gvox) + (size_t)s * kSlabBytes, kSlabBytes,
+                &sm.mbar[s & 1]);
+}
+// Slab s -> occupancy bytes; v_or / o_and accumulate "any voxel" / "all voxels" per thread.
+__device__ __forceinline__ void convert_ring_slab_c(SmemC& sm, int s, uint32_t& v_or, uint32_t& o_and) {
+    const int tid = threadIdx.x;
+    const uint4* slab = reinterpret_cast<const uint4*>(sm.tile.ring[s & 1]);
+    unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
+    uint4 q[4];
+    uint32_t slab_or = 0, slab_and = kFull;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        q[k] = slab[tid + k * kThreads];
+        slab_or |= q[k].x | q[k].y | q[k].z | q[k].w;
+        slab_and &= q[k].x & q[k].y & q[k].z & q[k].w;
+    }
+    v_or |= slab_or;
+    // the warp's 8 x 4 rows hold one value (air, or one kind of rock): nothing to gather bit by bit
+    const uint32_t first = __shfl_sync(kFull, slab_or, 0);
+    const bool same = slab_or == slab_and && (slab_or & 0xFFFFu) == (slab_or >> 16) && slab_or == first;
+    uint32_t ob = 0;
+    if (__all_sync(kFull, same)) {
+        ob = slab_or ? kFull : 0u;
+        o_and &= ob & 0xFFu;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t bits = nz8(q[k]);
+            o_and &= bits;
+            ob |= bits << (8 * k);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = tid + k * kThreads;
+        const int row = s * 256 + (idx >> 2), p = idx & 3;      // row = z*32 + y
+        occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)(ob >> (8 * k));
+    }
+}
+
+// v4::culled_emit with the word list cut into windows of PostC::kWordCap words.
+template <class IdFn>
+__device__ __forceinline__ void culled_emit_c(SmemC& sm, uint32_t mi, uint32_t packed, const MeshOut& out, IdFn id_of, Prof& prof) {
+    const int tid = threadIdx.x;
+    constexpr uint32_t kCap = PostC::kCap, kWordCap = PostC::kWordCap;
+    PostC& P = sm.tile.post;
+    uint32_t* const staging = P.staging;
+    auto nothing = [] {};
+    auto staged = [staging](uint32_t i) { return staging[i]; };
+    const int y = tid & 31, w = tid >> 5;
+    uint32_t tot;
+    const uint32_t pre = block_excl_scan(packed, sm.scratch, &tot);
+    const uint32_t Q = tot & 0x1FFFFu, nwords = tot >> 17;
+    if (Q == 0) {
+        if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};
+        prof.count(10);
+        return;
+    }
+    prof.count(11);
+    unsigned long long fq = 0;
+    if (tid == 0) fq = reserve_quads(sm, out, Q);   // in flight while the records are staged
+    bool first_flush = true;
+    for (uint32_t wbase = 0; wbase < nwords; wbase += kWordCap) {
+        const uint32_t wend = min(nwords, wbase + kWordCap);
+        if (wbase) __syncthreads();                 // the previous window's words have been expanded
+        {
+            uint32_t ord = pre & 0x1FFFFu, slot = pre >> 17;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t wd[6];
+                const int z = 4 * w + k;
+                if (!row_words_yz(sm, y, z, wd)) continue;
+                row_words_x(sm, y, z, wd);
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    if (wd[f]) {
+                        if (slot >= wbase && slot < wend) P.words[slot - wbase] = make_uint2((uint32_t)(f << 10 | y << 5 | z) | ord << 13, wd[f]);
+                        ++slot;
+                    }
+                    ord += __popc(wd[f]);
+                }
+            }
+        }
+        __syncthreads();
+        prof.mark(5);
+        const uint32_t wcount = wend - wbase;
+        const uint32_t ord_lo = P.words[0].x >> 13;
+        const uint2 lastw = P.words[wcount - 1];
+        const uint32_t ord_hi = (lastw.x >> 13) + __popc(lastw.y);
+        for (uint32_t base = ord_lo; base < ord_hi; base += kCap) {
+            const uint32_t end = min(ord_hi, base + kCap);
+            for (uint32_t i = tid; i < wcount; i += kThreads) {     // neighbours in the list are words of similar density
+                const uint2 d = P.words[i];
+                uint32_t bits = d.y, o = d.x >> 13;
+                if (o + __popc(bits) <= base || o >= end) continue;
+                const uint32_t f = (d.x >> 10) & 7u, yy = (d.x >> 5) & 31u, zz = d.x & 31u;
+                // u | v<<5 | s<<10 | f<<15:  X planes (s,u,v) = (x,y,z);  Y planes (y,x,z);  Z planes (z,x,y)
+                const uint32_t rb = f << 15 | (f < 2 ? (yy | zz << 5) : f < 4 ? (zz << 5 | yy << 10) : (yy << 5 | zz << 10));
+                const uint32_t sh = f < 2 ? 10u : 0u;
+                while (bits) {
+                    const uint32_t x = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (o >= base && o < end) staging[o - base] = rb | x << sh;
+                    ++o;
+                }
+            }
+            __syncthreads();
+            prof.mark(6);
+            bool fits;
+            if (first_flush) fits = flush_staging(sm, staged, end - base, base, out, id_of, [&] { if (tid == 0) publish_range(sm, mi, Q, fq, out); }, true);
+            else fits = flush_staging(sm, staged, end - base, base, out, id_of, nothing, false);
+            first_flush = false;
+            if (!fits) return;
+            __syncthreads();
+            prof.mark(7);
+        }
+    }
+}
+
+__device__ __forceinline__ void mesh_chunk_c(SmemC& sm, const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6,
+                                             uint32_t n, uint32_t chunk, uint32_t mi, const MeshOut& out, const Bnd& bnd) {
+    const int tid = threadIdx.x;
+    const uint16_t* gvox = voxels + (size_t)chunk * VXP_CHUNK_VOXELS;
+    Prof prof;
+    prof.start(tid == 0);
+    if (tid == 0) {
+        issue_ring_slab_c(sm, gvox, 0);
+        issue_ring_slab_c(sm, gvox, 1);
+    }
+    const int nb = (nbr6 && tid < 192) ? __ldg(nbr6 + 6 * (size_t)chunk + (tid >> 5)) : -1;
+    HaloRows rows;
+    issue_yz_halo(rows, voxels, nb);
+    uint32_t v_or = 0, o_and = kFull;
+#pragma unroll 1
+    for (int s = 0; s < kSlabs; ++s) {
+        mbar_wait(&sm.mbar[s & 1], (uint32_t)(s >> 1) & 1u);
+        convert_ring_slab_c(sm, s, v_or, o_and);
+        if (s + 2 < kSlabs) {
+            __syncthreads();                            // the buffer has been read by everybody
+            if (tid == 0) issue_ring_slab_c(sm, gvox, s + 2);
+        }
+    }
+    prof.mark(0);
+    ChunkFlags fl;
+    fl.any_solid = __syncthreads_or(v_or != 0u);        // barrier: occupancy interior published, ring dead
+    fl.all_solid = __syncthreads_and((o_and & 0xFFu) == 0xFFu);
+    fl.single_id = fl.small_ids = false;
+    prof.mark(1);
+    if (bnd.tags) publish_boundary(sm, bnd, chunk, fl);
+    if (!fl.any_solid) {
+        if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};
+        prof.count(8);
+        return;
+    }
+    auto id_of = [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); };
+    XPoll xp;
+    if (!fl.all_solid) {
+        // count the faces that do not depend on the x halo (+-Y, +-Z) while the x neighbours' boundary planes are on their way
+        halo_begin(sm, nb, n, bnd, rows, xp);
+        __syncthreads();                                // +-Y / +-Z halo rows published
+        uint32_t packed = culled_count<false>(sm);
+        halo_finish(sm, voxels, nb, n, bnd, xp, prof);
+        __syncthreads();                                // x halo published
+        prof.mark(2);
+        packed += culled_count<true>(sm);
+        culled_emit_c(sm, mi, packed, out, id_of, prof);
+        return;
+    }
+    const bool air_yz = halo_begin(sm, nb, n, bnd, rows, xp);
+    const bool air_x = halo_finish(sm, voxels, nb, n, bnd, xp, prof);
+    const bool halo_air = __syncthreads_or(air_yz || air_x);   // barrier: halo published
+    prof.mark(2);
+    if (!halo_air) {                                    // buried: no faces
+        if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};
+        prof.count(9);
+        return;
+    }
+    culled_emit_c(sm, mi, culled_count<false>(sm) + culled_count<true>(sm), out, id_of, prof);
+}
+
+// Same contract and launch chaining as v4::mesh_kernel<false>.
+#ifndef VXP_CULLED_CTAS
+#define VXP_CULLED_CTAS 4
+#endif
+__global__ void __launch_bounds__(kThreads, VXP_CULLED_CTAS)
+mesh_kernel_c(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, uint32_t chunk0, uint32_t hi,
+              MeshOut out, Bnd bnd, Chain chain) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemC& sm = *reinterpret_cast<SmemC*>(smem_raw);
+    const bool dealt = chain.runs != 0u && (blockIdx.x >> 4) < chain.runs;
+    if (dealt && threadIdx.x == 0)
+        sm.cursor = (uint32_t)(((unsigned long long)(blockIdx.x >> 4) * chain.run_stride) % chain.runs) * 16u + (blockIdx.x & 15u);
+    const bool closer = chain.user_total != nullptr && blockIdx.x == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        if (closer) griddep_wait();
+        sm.counted = 0u;
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    griddep_launch_dependents();
+    uint32_t chunk = dealt ? sm.cursor : chunk0 + blockIdx.x;
+    uint32_t mi = chunk;
+    bool active = chunk < hi;
+    if (chain.list != nullptr) {
+        active = chain.list_count == nullptr || blockIdx.x < __ldg(chain.list_count);
+        chunk = active ? __ldg(chain.list + blockIdx.x) : 0u;
+        mi = blockIdx.x;
+        active = active && chunk < n;
+    }
+    if (active) mesh_chunk_c(sm, voxels, nbr6, n, chunk, mi, out, bnd);
+    if (threadIdx.x == 0 && chain.user_total != nullptr) {
+        if (!sm.counted) red_add_u64(out.total, kCtaOne);
+        if (closer) {
+            unsigned long long t;
+            while (((t = ld_relaxed_u64(out.total)) >> kQuadBits) != gridDim.x) __nanosleep(64);
+            *chain.user_total = t & kQuadMask;
+            st_relaxed_u64(out.total, 0ull);
+        }
+    }
+}
+
 } // namespace v5
 } // namespace vxp
