@@ -881,8 +881,10 @@ __device__ __forceinline__ void mesh_chunk_c(SmemC& sm, const uint16_t* __restri
 }
 
 // Same contract and launch chaining as v4::mesh_kernel<false>.
+// CTAs per SM the kernel is compiled for (measured on config 2: 3 = generation 4: 69.5 us; 4: 65.4 us at 61 registers;
+// 5: 62.4 us at 48 registers, no spills; the shared memory would allow six, the registers would not)
 #ifndef VXP_CULLED_CTAS
-#define VXP_CULLED_CTAS 4
+#define VXP_CULLED_CTAS 5
 #endif
 __global__ void __launch_bounds__(kThreads, VXP_CULLED_CTAS)
 mesh_kernel_c(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, uint32_t chunk0, uint32_t hi,
