@@ -338,9 +338,9 @@ def main():
     achieved = mean_bytes / (mean_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
     # (profiles/r1_ncu_*_summary.txt); None for workloads that were not captured
-    ncu_traffic = {"terrain_culled": 276.8e6 + 75.5e6, "terrain_greedy": 278.3e6 + 27.2e6}.get(args.workload)
+    ncu_traffic = {"terrain_culled": 289.5e6 + 68.7e6, "terrain_greedy": 278.3e6 + 27.2e6}.get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic, "peak_source": peak_src, "kernel": ("v5::mesh_kernel_g" if mode == GREEDY else "v4::mesh_kernel<0>") if not fused else "terrain_mesh_kernel_g",
+                "traffic": ncu_traffic, "peak_source": peak_src, "kernel": ("v5::mesh_kernel_g" if mode == GREEDY else "v5::mesh_kernel_c") if not fused else "terrain_mesh_kernel_g",
                 "kernel_ms_mean": mean_ms, "algorithmic_bytes_per_launch": mean_bytes, "launches_timed": args.steps,
                 "overlap": overlap,
                 "isolated": {"kernel_ms_mean": statistics.mean(iso_ms), "kernel_ms_min": min(iso_ms), "launches": iso_n,
