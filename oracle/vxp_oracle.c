@@ -334,6 +334,75 @@ void vxo_mesh_batch_hash(const uint16_t *vox, const int32_t *nbr, uint32_t n, in
     vxo_parallel_for(n, threads, 4, hash_body, &c);
 }
 
+
+/* ------------------------------------------- terrain world (fused path, config 5) */
+
+typedef struct {
+    uint64_t seed;
+    int32_t x0, y0, w; /* origin and row width of the layer, halo ring included */
+    int32_t cz;
+    uint16_t *dst;
+} layer_ctx;
+
+static void layer_body(void *p, int64_t i, uint64_t *scratch) {
+    layer_ctx *c = (layer_ctx *)p;
+    (void)scratch;
+    vxo_terrain_fill(c->seed, c->x0 + (int32_t)(i % c->w), c->y0 + (int32_t)(i / c->w), c->cz,
+                     c->dst + (size_t)i * VXO_VOXELS);
+}
+
+typedef struct {
+    const uint16_t *prev, *cur, *next; /* layers cz-1, cz, cz+1, each (nx+2) x (ny+2) chunks */
+    int32_t nx, w;
+    int mode;
+    uint64_t *hashes;
+    uint32_t *counts;
+} world_ctx;
+
+static void world_body(void *p, int64_t i, uint64_t *keys) {
+    world_ctx *c = (world_ctx *)p;
+    size_t j = (size_t)(i % c->nx + 1) + (size_t)c->w * (size_t)(i / c->nx + 1);
+    const uint16_t *nb[6] = {c->cur + (j - 1) * VXO_VOXELS,          c->cur + (j + 1) * VXO_VOXELS,
+                             c->cur + (j - (size_t)c->w) * VXO_VOXELS, c->cur + (j + (size_t)c->w) * VXO_VOXELS,
+                             c->prev + j * VXO_VOXELS,                c->next + j * VXO_VOXELS};
+    uint32_t cnt = vxo_mesh_chunk_keys(c->cur + j * VXO_VOXELS, nb, c->mode, keys);
+    c->counts[i] = cnt;
+    c->hashes[i] = vxo_hash_keys(keys, cnt);
+}
+
+int vxo_terrain_world_hash(uint64_t seed, const int32_t lo[3], const int32_t hi[3], int mode, int threads,
+                           uint64_t *hashes, uint32_t *counts) {
+    const int32_t nx = hi[0] - lo[0], ny = hi[1] - lo[1], nz = hi[2] - lo[2];
+    if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+    const int32_t w = nx + 2;
+    const size_t layer_chunks = (size_t)w * (size_t)(ny + 2);
+    uint16_t *buf[3];
+    for (int k = 0; k < 3; ++k) {
+        buf[k] = (uint16_t *)malloc(layer_chunks * VXO_VOXELS * sizeof(uint16_t));
+        if (!buf[k]) {
+            for (int j = 0; j < k; ++j) free(buf[j]);
+            return -1;
+        }
+    }
+    /* every chunk is generated with the plain per-chunk fill, neighbours included: no shortcut of any kind */
+    layer_ctx lc = {seed, lo[0] - 1, lo[1] - 1, w, 0, NULL};
+    for (int k = 0; k < 2; ++k) { /* layers lo.z - 1 and lo.z */
+        lc.cz = lo[2] - 1 + k;
+        lc.dst = buf[k];
+        vxo_parallel_for((int64_t)layer_chunks, threads, 8, layer_body, &lc);
+    }
+    for (int32_t z = 0; z < nz; ++z) {
+        uint16_t *prev = buf[z % 3], *cur = buf[(z + 1) % 3], *next = buf[(z + 2) % 3];
+        lc.cz = lo[2] + z + 1;
+        lc.dst = next;
+        vxo_parallel_for((int64_t)layer_chunks, threads, 8, layer_body, &lc);
+        world_ctx wc = {prev, cur, next, nx, w, mode, hashes + (size_t)z * nx * ny, counts + (size_t)z * nx * ny};
+        vxo_parallel_for((int64_t)nx * ny, threads, 4, world_body, &wc);
+    }
+    for (int k = 0; k < 3; ++k) free(buf[k]);
+    return 0;
+}
+
 int vxo_max_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n < 1 ? 1 : (int)n;

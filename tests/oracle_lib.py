@@ -42,6 +42,8 @@ def load() -> C.CDLL:
     lib.vxo_mesh_batch_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p]
     lib.vxo_max_threads.restype = C.c_int
+    lib.vxo_terrain_world_hash.restype = C.c_int
+    lib.vxo_terrain_world_hash.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -124,4 +126,18 @@ def mesh_batch_hash(vox: np.ndarray, nbr6, mode: int, threads: int = 0):
     counts = np.empty(n, dtype=np.uint32)
     load().vxo_mesh_batch_hash(vox.ctypes.data, nptr, n, mode, threads or max_threads(), hashes.ctypes.data,
                                counts.ctypes.data)
+    return hashes, counts
+
+
+def terrain_world_hash(seed, lo, hi, mode: int, threads: int = 0):
+    """(hashes u64, counts u32) of the chunks of the box [lo, hi) of the infinite terrain, x-fastest order."""
+    lo = np.ascontiguousarray(lo, dtype=np.int32)
+    hi = np.ascontiguousarray(hi, dtype=np.int32)
+    n = int(np.prod(np.maximum(hi - lo, 0)))
+    hashes = np.empty(n, dtype=np.uint64)
+    counts = np.empty(n, dtype=np.uint32)
+    rc = load().vxo_terrain_world_hash(seed & (2**64 - 1), lo.ctypes.data, hi.ctypes.data, mode, threads or max_threads(),
+                                       hashes.ctypes.data, counts.ctypes.data)
+    if rc != 0:
+        raise MemoryError("vxo_terrain_world_hash")
     return hashes, counts

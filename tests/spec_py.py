@@ -199,6 +199,27 @@ def expand_quad(key: int, q: int):
 # ----------------------------------------------------------------- numpy helpers
 # Vectorised decoders used by the GPU parity tests (not part of the restatement).
 
+def expand_keys(keys: np.ndarray) -> np.ndarray:
+    """SPEC §5 for an array of canonical keys at once: (Q,4) u64 vertices (vectorised expand_quad)."""
+    k = np.asarray(keys, dtype=np.uint64).astype(np.int64)
+    u, v, s = k & 63, (k >> 6) & 63, (k >> 12) & 63
+    f, w, h = (k >> 18) & 7, ((k >> 21) & 31) + 1, ((k >> 26) & 31) + 1
+    b = (k >> 31) & 0xFFFF
+    axis, along = f >> 1, s + (f & 1)
+    flip = (f == 0) | (f == 3) | (f == 4)
+    cu = np.stack([u, u + w, u + w, u], axis=1)          # corners c0..c3
+    cv = np.stack([v, v, v + h, v + h], axis=1)
+    order = np.where(flip[:, None], np.array([0, 3, 2, 1]), np.array([0, 1, 2, 3]))
+    cu, cv = np.take_along_axis(cu, order, 1), np.take_along_axis(cv, order, 1)
+    a, al = axis[:, None], along[:, None]
+    x = np.where(a == 0, al, cu)
+    y = np.where(a == 0, cu, np.where(a == 1, al, cv))
+    z = np.where(a == 2, al, cv)
+    w0 = x | y << 6 | z << 12 | f[:, None] << 18 | np.arange(4)[None, :] << 21
+    w1 = (b | (w - 1) << 16 | (h - 1) << 21)[:, None]
+    return (w0 | w1 << 32).astype(np.uint64)
+
+
 def keys_from_verts(verts: np.ndarray) -> np.ndarray:
     """Recover canonical keys from a (Q,4) u64 vertex array (SPEC §5 inverse)."""
     verts = np.asarray(verts, dtype=np.uint64).reshape(-1, 4)

@@ -37,6 +37,74 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert set(names) == set(L.SIGNATURES), set(names) ^ set(L.SIGNATURES)
 
 
+def test_exports_are_exactly_the_header(lib):
+    """No undeclared vxp_* entry point ships: the dynamic symbols of libvxp.so are the functions of include/vxp.h
+    (debug / profiling exports exist only in the `make prof` / `make variant` builds)."""
+    import voxelphile_b200._lib as L
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(line.split()[-1] for line in out.splitlines() if line.split()[-1].startswith("vxp_"))
+    assert exported == declared_functions(), set(exported) ^ set(declared_functions())
+
+
+def test_library_has_no_runtime_switches():
+    """No environment variable changes what the shipped library runs (no multi-path dispatch): tuning variants are
+    separate `make variant` builds."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "voxelphile_b200", "csrc")):
+        for f in files:
+            assert "getenv" not in open(os.path.join(dirpath, f), errors="ignore").read(), f
+
+
+def build_c_consumer(tmpdir):
+    """tests/c_consumer/consumer.c compiled as strict C11 against include/vxp.h and linked (not dlopen'd) with libvxp.so."""
+    import voxelphile_b200._lib as L
+    exe = os.path.join(str(tmpdir), "vxp_consumer")
+    libdir = os.path.dirname(L.LIB_PATH)
+    link = os.path.join(str(tmpdir), "libvxp.so")
+    if not os.path.exists(link):
+        os.symlink(L.LIB_PATH, link)
+    subprocess.run(["gcc", "-std=c11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_consumer", "consumer.c"), "-L", str(tmpdir), "-lvxp",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_c11_consumer_compiles_links_and_fails_loudly_without_a_device(lib, tmp_path):
+    import torch
+    exe = build_c_consumer(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the run is checked by the gpu test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_c11_consumer_matches_the_oracle(lib, tmp_path):
+    """The linked C program's meshes (stored and fused, both modes) against the oracle on the same coordinates."""
+    import oracle_lib as O
+    exe = build_c_consumer(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    coords = np.array([[0, 0, 0], [0, 8, 0], [1, 8, 0]], dtype=np.int32)
+    from voxelphile_b200 import neighbour_table
+    nbr = neighbour_table(coords)
+    vox = O.terrain_fill_batch(42, coords)
+    want = {}
+    for mode in (0, 1):
+        h, c = O.mesh_batch_hash(vox, nbr, mode)
+        for i in range(3):
+            want[("stored", mode, i)] = (int(c[i]), int(h[i]))
+            lo = tuple(int(v) for v in coords[i])
+            fh, fc = O.terrain_world_hash(42, lo, tuple(v + 1 for v in lo), mode)
+            want[("fused", mode, i)] = (int(fc[0]), int(fh[0]))
+    got = {}
+    for line in r.stdout.split("\n"):
+        if line.strip():
+            call, mode, i, cnt, h = line.split()
+            got[(call, int(mode), int(i))] = (int(cnt), int(h))
+    assert got == want
+    assert sum(c for c, _ in got.values()) > 0
+
+
 def test_library_is_sm100a_only():
     import voxelphile_b200._lib as L
     out = subprocess.run(["cuobjdump", "-lelf", L.LIB_PATH], capture_output=True, text=True).stdout

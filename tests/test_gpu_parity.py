@@ -73,12 +73,12 @@ def check_against_oracle(host, vox, nbr, mode, expect_keys=None):
         got = S.keys_from_verts(v)
         order = np.argsort(got, kind="stable")
         assert np.array_equal(got[order], want), f"chunk {i}: key sets differ"
-        # vertex bytes: expand the oracle's quads and compare in key order
-        ref_v = np.empty((cnt, 4), dtype=np.uint64)
-        step = max(1, cnt // 512)          # full check on small meshes, strided sample on huge ones
-        for q in range(0, cnt, step):
-            ref_v[q], _ = O.expand_quad(int(want[q]), 0)
-            assert np.array_equal(v[order[q]], ref_v[q]), (i, q)
+        # vertex bytes of EVERY quad, in key order, against the SPEC §5 expansion of the oracle's keys (the numpy
+        # expansion is itself checked against the oracle's C expansion: tests/test_oracle.py); a sample through the
+        # oracle's own vxo_expand_quad on top
+        assert np.array_equal(v[order], S.expand_keys(want)), f"chunk {i}: vertex bytes"
+        for q in range(0, cnt, max(1, cnt // 64)):
+            assert np.array_equal(v[order[q]], O.expand_quad(int(want[q]), 0)[0]), (i, q)
         # every vertex of every quad carries the same (f, id, w, h) and corner numbers 0..3
         w0 = (v & np.uint64(0xFFFFFFFF)).astype(np.int64)
         assert np.array_equal((w0 >> 21) & 3, np.tile(np.arange(4), (cnt, 1)))
@@ -195,15 +195,12 @@ def test_terrain_block_stored_path(mesher, mode, mname):
     check_against_oracle(out.to_host(), vox, nbr, mode)
 
 
-@pytest.mark.parametrize("mode,mname", MODES + [(1, "greedy_generation5")])
-def test_fused_terrain_mesh(mesher, mode, mname, monkeypatch):
-    """Fused path: neighbours are the infinite terrain itself.  Large greedy batches run the four-CTA kernel
-    (generation 5); VXP_FUSED_V5 selects it for this small one too."""
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_fused_terrain_mesh(mesher, mode, mname):
+    """Fused path: neighbours are the infinite terrain itself."""
     import torch
     from voxelphile_b200 import grid_coords
     seed = 42
-    if mname == "greedy_generation5":
-        monkeypatch.setenv("VXP_FUSED_V5", "1")
     coords = np.concatenate([grid_coords((0, 6, 0), (3, 10, 2)), np.array([[-7, 8, 3], [5, 0, 5], [5, 30, 5]], np.int32)])
     out = mesher.terrain_mesh(dev(coords), seed, mode, capacity=coords.shape[0] * 8192)
     torch.cuda.synchronize()
@@ -340,21 +337,22 @@ def _chunk_hashes(host):
 
 
 @pytest.mark.parametrize("mode,mname", MODES)
-def test_full_size_batch_hash_parity(mesher, mode, mname):
-    """BASELINE configs 2 / 3 at full size (4096 terrain chunks, coords [0,16)^3, seed 42): per-chunk quad
-    counts and order-independent key hashes equal the oracle's for every chunk, through the device-level
-    call and through the sliced host-level call."""
+@pytest.mark.parametrize("seed", [42, 43, 44, 45])
+def test_full_size_batch_hash_parity(mesher, mode, mname, seed):
+    """BASELINE configs 2 / 3 at full size (4096 terrain chunks, coords [0,16)^3), for every seed bench.py times
+    (42..45): per-chunk quad counts and order-independent key hashes equal the oracle's for every chunk, through
+    the device-level call and (seed 42) through the sliced host-level call."""
     import torch
     from voxelphile_b200 import grid_coords, neighbour_table
     coords = grid_coords((0, 0, 0), (16, 16, 16))
     nbr = neighbour_table(coords)
-    dvox = mesher.terrain_fill(dev(coords), 42)
+    dvox = mesher.terrain_fill(dev(coords), seed)
     torch.cuda.synchronize()
     vox = dvox.cpu().numpy().view(np.uint16)
     want_hash, want_cnt = O.mesh_batch_hash(vox, nbr, mode)
     out = mesher.mesh(dvox, dev(nbr), mode, capacity=int(want_cnt.sum()))
     torch.cuda.synchronize()
-    for host in (out.to_host(), mesher.mesh_host(vox, nbr, mode)):
+    for host in (out.to_host(),) + ((mesher.mesh_host(vox, nbr, mode),) if seed == 42 else ()):
         assert host.total_quads == int(want_cnt.sum())
         assert np.array_equal(host.meta[:, 1], want_cnt)
         assert np.array_equal(_chunk_hashes(host), want_hash)
@@ -657,29 +655,111 @@ def test_mesh_packed_host_equals_mesh_host(mesher, mode, mname):
     _check_remeshed(host, dirty.astype(np.int64), vox, nbr, mode)
 
 
-def test_fused_world_generation5_matches_generation4(mesher, monkeypatch):
-    """A batch large enough for the four-CTA fused kernel (32 768 chunks): per-chunk counts and key hashes equal
-    those of the same call forced through the small-batch kernel in slices, and the oracle on sampled chunks."""
+def test_fused_world_full_size(mesher):
+    """BASELINE config 5 at full size: the 65^3 = 274 625 chunk coordinates centred on the origin, seed 42, fused
+    terrain + greedy: per-chunk quad counts and key hashes of EVERY chunk against the oracle, which generates and
+    meshes the world one z-layer at a time (vxo_terrain_world_hash)."""
     import torch
     from voxelphile_b200 import grid_coords
-    coords = grid_coords((-16, -8, -16), (16, 24, 16))
-    assert coords.shape[0] == 32768
-    big = mesher.terrain_mesh(dev(coords), 42, 1, capacity=4_000_000)
+    lo, hi = (-32, -32, -32), (33, 33, 33)
+    coords = grid_coords(lo, hi)
+    assert coords.shape[0] == 274625
+    want_hash, want_cnt = O.terrain_world_hash(42, lo, hi, 1)
+    out = mesher.terrain_mesh(dev(coords), 42, 1, capacity=int(want_cnt.sum()))
     torch.cuda.synchronize()
-    hb = big.to_host()
-    hashes = _chunk_hashes(hb)
-    for lo in range(0, 32768, 8192):                              # 8192 < 32768: generation 4
-        part = mesher.terrain_mesh(dev(coords[lo:lo + 8192]), 42, 1, capacity=2_000_000)
+    host = out.to_host()
+    assert host.total_quads == int(want_cnt.sum())
+    assert np.array_equal(host.meta[:, 1], want_cnt)
+    assert np.array_equal(_chunk_hashes(host), want_hash)
+    # a second call on the same context (next key epoch of the column table, counters left zeroed by the first)
+    out2 = mesher.terrain_mesh(dev(coords), 42, 1, capacity=int(want_cnt.sum()))
+    torch.cuda.synchronize()
+    host2 = out2.to_host()
+    assert np.array_equal(host2.meta[:, 1], want_cnt) and np.array_equal(_chunk_hashes(host2), want_hash)
+
+
+def test_fused_world_slab_culled_and_shuffled(mesher):
+    """Six z-layers of the config-5 world (25 350 chunks) through the fused culled kernel, and the same chunks in a
+    shuffled order through the fused greedy kernel (columns are found through the hash table, not by position)."""
+    import torch
+    from voxelphile_b200 import grid_coords
+    lo, hi = (-32, -32, -3), (33, 33, 3)
+    coords = grid_coords(lo, hi)
+    for mode in (0, 1):
+        want_hash, want_cnt = O.terrain_world_hash(42, lo, hi, mode)
+        perm = np.random.default_rng(5).permutation(coords.shape[0]) if mode == 1 else np.arange(coords.shape[0])
+        out = mesher.terrain_mesh(dev(coords[perm]), 42, mode, capacity=int(want_cnt.sum()))
         torch.cuda.synchronize()
-        hp = part.to_host()
-        assert np.array_equal(hp.meta[:, 1], hb.meta[lo:lo + 8192, 1])
-        assert np.array_equal(_chunk_hashes(hp), hashes[lo:lo + 8192])
-    surface = np.nonzero(hb.meta[:, 1])[0]
-    for i in surface[:: max(1, len(surface) // 12)]:
-        c = tuple(map(int, coords[i]))
-        nbs = [O.terrain_fill(42, c[0] + d[0], c[1] + d[1], c[2] + d[2]) for d in S.DIRS]
-        want = O.mesh_chunk_keys(O.terrain_fill(42, *c), nbs, 1)
-        assert np.array_equal(np.sort(S.keys_from_verts(hb.chunk(int(i))[0])), want), c
+        host = out.to_host()
+        assert np.array_equal(host.meta[:, 1], want_cnt[perm]), mode
+        assert np.array_equal(_chunk_hashes(host), want_hash[perm]), mode
+
+
+def _device_chunk_hashes(out, n):
+    """_chunk_hashes on the device (torch as the checker's arithmetic) for meshes too large to bring to the host:
+    keys from vertex 0 of every quad (SPEC §5 inverse), mix64, per-chunk sums through a cumulative sum over the
+    chunk ranges.  Returns (hashes u64 numpy, counts, ranges_tile)."""
+    import torch
+    Q = int(out.total.item())
+    meta = out.meta.cpu().numpy().view(np.uint32).reshape(n, 2)
+    first, cnt = meta[:, 0].astype(np.int64), meta[:, 1].astype(np.int64)
+    v0 = out.verts[: 4 * Q].view(-1, 4)[:, 0]
+    w0, w1 = v0 & 0xFFFFFFFF, (v0 >> 32) & 0xFFFFFFFF
+    x, y, z, f = w0 & 63, (w0 >> 6) & 63, (w0 >> 12) & 63, (w0 >> 18) & 7
+    axis = f >> 1
+    along = torch.where(axis == 0, x, torch.where(axis == 1, y, z)) - (f & 1)
+    u = torch.where(axis == 0, y, x)
+    v = torch.where(axis == 2, y, z)
+    key = u | v << 6 | along << 12 | f << 18 | ((w1 >> 16) & 31) << 21 | ((w1 >> 21) & 31) << 26 | (w1 & 0xFFFF) << 31
+    del w0, w1, x, y, z, f, axis, along, u, v
+
+    def shr(t, k):                                                   # logical shift of the u64 bit pattern held in int64
+        return (t >> k) & ((1 << (64 - k)) - 1)
+
+    def c64(c):                                                      # u64 constant as the int64 with the same bits
+        return c - (1 << 64) if c >= (1 << 63) else c
+
+    zt = key + c64(0x9E3779B97F4A7C15)
+    zt = (zt ^ shr(zt, 30)) * c64(0xBF58476D1CE4E5B9)
+    zt = (zt ^ shr(zt, 27)) * c64(0x94D049BB133111EB)
+    zt = zt ^ shr(zt, 31)
+    cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=zt.device), torch.cumsum(zt, 0)])
+    fi = torch.from_numpy(first).to(zt.device)
+    ci = torch.from_numpy(cnt).to(zt.device)
+    fi = torch.where(ci > 0, fi, torch.zeros_like(fi))
+    h = (cs[fi + ci] - cs[fi]).cpu().numpy().view(np.uint64)
+    nz = cnt > 0
+    order = np.argsort(first[nz])
+    f_s, c_s = first[nz][order], cnt[nz][order]
+    tiles = len(f_s) == 0 or (f_s[0] == 0 and np.array_equal(f_s[1:], np.cumsum(c_s)[:-1]) and f_s[-1] + c_s[-1] == Q)
+    return h, cnt, tiles
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_checkerboard_full_size(mesher, mode, mname):
+    """BASELINE config 4 at the size bench.py times: 4096 chunks ([0,16)^3) of the world-parity checkerboard,
+    402 653 184 quads (22.5 GB of mesh).  Every chunk: 98 304 quads and the oracle's key hash; the ranges tile
+    [0, Q); the indices of a sampled range are the chunk-local ordinals."""
+    import torch
+    from voxelphile_b200 import grid_coords, neighbour_table, PATTERN_CHECKER
+    coords = grid_coords((0, 0, 0), (16, 16, 16))
+    nbr = neighbour_table(coords)
+    dvox = mesher.pattern_fill(dev(coords), PATTERN_CHECKER)
+    torch.cuda.synchronize()
+    vox = dvox.cpu().numpy().view(np.uint16)
+    want_hash, want_cnt = O.mesh_batch_hash(vox, nbr, mode)
+    assert (want_cnt == 98304).all()
+    out = mesher.mesh(dvox, dev(nbr), mode, capacity=4096 * 98304)
+    torch.cuda.synchronize()
+    assert int(out.total.item()) == 4096 * 98304
+    h, cnt, tiles = _device_chunk_hashes(out, 4096)
+    assert (cnt == 98304).all() and tiles
+    assert np.array_equal(h, want_hash)
+    first = int(out.meta[1234, 0].item())
+    ix = out.indices[6 * first: 6 * (first + 98304)].cpu().numpy().view(np.uint32).reshape(-1, 6)
+    assert np.array_equal(ix, 4 * np.arange(98304, dtype=np.uint32)[:, None] + np.array([0, 1, 2, 2, 3, 0], dtype=np.uint32))
+    del out
+    torch.cuda.empty_cache()
 
 
 def test_greedy_staging_fallbacks(mesher):
@@ -738,22 +818,59 @@ def test_downsample_and_mesh_lod(mesher):
         level, dim = want, half
 
 
-def test_terrain_fill_large_batches_bit_exact(mesher, monkeypatch):
-    """Large batches (>= 16 384 chunks; VXP_FILL_COLUMNS selects it for these smaller ones) take the shared-column
-    path of vxp_terrain_fill_batch: a tall block (16 chunks per column), a flat sheet (every column its own) and a
-    shuffled list with negative coordinates, against the oracle."""
+def test_terrain_fill_large_batches_bit_exact(mesher):
+    """Batches of >= 16 384 chunks take the shared-column path of vxp_terrain_fill_batch: one batch of 17 216 chunks
+    made of a tall block (16 chunks per column), a flat sheet (every column its own) and a shuffled list with
+    negative coordinates (some columns shared with the block), against the oracle; then a smaller batch (direct
+    path) on the same context, and the large one again (next epoch of the column table)."""
     import torch
     from voxelphile_b200 import grid_coords
-    monkeypatch.setenv("VXP_FILL_COLUMNS", "1")
     rng = np.random.default_rng(13)
-    tall = grid_coords((0, 0, 0), (8, 16, 8))                        # 1024 chunks, 64 columns
-    sheet = grid_coords((-20, 8, -20), (20, 9, 20))                  # 1600 chunks, 1600 columns
-    mixed = grid_coords((-6, 4, -6), (6, 13, 6))                     # 1296 chunks
+    tall = grid_coords((0, 0, 0), (24, 16, 24))                      # 9216 chunks, 576 columns
+    sheet = grid_coords((-70, 8, -40), (-10, 9, 20))                 # 3600 chunks, 3600 columns
+    mixed = grid_coords((-10, 2, -10), (10, 13, 10))                 # 4400 chunks
     mixed = mixed[rng.permutation(mixed.shape[0])]
-    for seed, coords in ((42, tall), (7, sheet), (2**63 + 5, mixed)):
+    coords = np.concatenate([tall, sheet, mixed])
+    assert coords.shape[0] >= 16384
+    seed = 2**63 + 5
+    want = O.terrain_fill_batch(seed, coords)
+    for rep in range(2):
         got = mesher.terrain_fill(dev(coords), seed)
         torch.cuda.synchronize()
-        assert np.array_equal(got.cpu().numpy().view(np.uint16), O.terrain_fill_batch(seed, coords)), seed
+        assert np.array_equal(got.cpu().numpy().view(np.uint16), want), rep
+        del got
+        small = mesher.terrain_fill(dev(coords[:1000]), seed)
+        torch.cuda.synchronize()
+        assert np.array_equal(small.cpu().numpy().view(np.uint16), want[:1000])
+    # the fused path right after the column fill (they share the column scratch and its launch counters)
+    fc = grid_coords((0, 6, 0), (3, 10, 2))
+    wh, wc = O.terrain_world_hash(42, (0, 6, 0), (3, 10, 2), 1)
+    out = mesher.terrain_mesh(dev(fc), 42, 1, capacity=int(wc.sum()))
+    torch.cuda.synchronize()
+    host = out.to_host()
+    assert np.array_equal(host.meta[:, 1], wc) and np.array_equal(_chunk_hashes(host), wh)
+
+
+def test_default_stream_configuration(G):
+    """A Mesher used as constructed (no use_current_torch_stream call): device tensors made on torch's stream, the
+    kernels on the stream the Mesher chose, results read back through torch - ordering is the Mesher's job."""
+    import torch
+    from voxelphile_b200 import Mesher
+    m = Mesher(0)
+    vox, nbr = G["terrain42/vox"], G["terrain42/nbr"]
+    want_h, want_c = O.mesh_batch_hash(vox, nbr, 1)
+    side = torch.cuda.Stream()
+    for rep in range(20):
+        with torch.cuda.stream(side if rep % 2 else torch.cuda.default_stream()):
+            dv = dev(vox.view(np.int16))
+            dn = dev(nbr)
+            junk = torch.full((1 << 22,), rep, dtype=torch.int64, device="cuda")   # keeps the allocating stream busy
+            out = m.mesh(dv, dn, 1, capacity=int(want_c.sum()))
+            host = out.to_host()
+            del junk
+        assert np.array_equal(host.meta[:, 1], want_c), rep
+        assert np.array_equal(_chunk_hashes(host), want_h), rep
+    m.close()
 
 
 def test_new_entry_points_reject_bad_arguments_and_accept_empty_batches(mesher):

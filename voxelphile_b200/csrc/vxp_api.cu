@@ -4,7 +4,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -28,7 +27,7 @@ struct vxp_ctx {
     uint64_t* d_verts = nullptr;    uint32_t* d_indices = nullptr; size_t quads_cap = 0;
     uint64_t* d_total = nullptr;
     // boundary-summary scratch of the mesh kernel (vxp_launch.h: BoundaryScratch)
-    // Two launch slots used alternately, so that consecutive launches share nothing (launch chaining, vxp_mesh4.cuh).
+    // Two launch slots used alternately, so that consecutive launches share nothing (launch chaining, vxp_mesh_common.cuh).
     uint32_t* d_tags[2] = {};       unsigned long long* d_planes[2] = {};    size_t bnd_cap = 0;   // chunks
     uint32_t epoch = 0;
     unsigned long long* d_counters = nullptr;   // one zero-initialised launch counter per slot
@@ -200,12 +199,14 @@ vxp_status chained_mesh_launch(vxp_ctx* ctx, const uint16_t* d_voxels, const int
     return VXP_OK;
 }
 
-// Column scratch for a fused launch over n chunks: one allocation carved into the ColumnScratch arrays.
+// Column scratch for a fused launch over n chunks: one allocation carved into the ColumnScratch arrays.  The hash
+// table and the launch counters are zeroed when allocated; every call gets the next key epoch (the table is
+// re-zeroed when the 10-bit epoch wraps), so calls start without a memset.
 vxp_status column_scratch(vxp_ctx* ctx, uint32_t n, vxp::ColumnScratch* out) {
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     if (n > ctx->columns_cap) {
         const size_t want = (size_t)n + n / 4;
         const size_t slots = vxp::column_table_slots((uint32_t)want);
-        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
         const size_t b_keys = up(slots * 8), b_ids = up(slots * 4), b_slot = up(want * 8), b_coord = up(want * 8),
                      b_h = up(want * vxp::column_record_bytes()), b_cnt = 256;
         if (ctx->d_columns) VXP_CUDA(ctx, cudaFree(ctx->d_columns));
@@ -220,7 +221,14 @@ vxp_status column_scratch(vxp_ctx* ctx, uint32_t n, vxp::ColumnScratch* out) {
         ctx->columns.heights = reinterpret_cast<short*>(p); p += b_h;
         ctx->columns.count = reinterpret_cast<uint32_t*>(p);
         ctx->columns.mask = (uint32_t)(slots - 1);
+        ctx->columns.epoch = 0;
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->columns.keys, 0, b_keys, ctx->stream));
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->columns.count, 0, b_cnt, ctx->stream));
         ctx->columns_cap = want;
+    }
+    if (++ctx->columns.epoch >= 1024u) {
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->columns.keys, 0, ((size_t)ctx->columns.mask + 1) * 8, ctx->stream));
+        ctx->columns.epoch = 1;
     }
     *out = ctx->columns;
     return VXP_OK;
@@ -473,7 +481,7 @@ vxp_status vxp_terrain_fill_batch(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
     if (!ctx || (n && (!d_coords || !d_voxels)) || !aligned16(d_voxels)) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     ctx->chain_open = false;
-    if ((n >= kColumnFillMin || getenv("VXP_FILL_COLUMNS")) && !getenv("VXP_FILL_DIRECT")) {   // large batch: the chunks of a column share its heights
+    if (n >= kColumnFillMin) {   // large batch: the chunks of a column share its heights
         vxp::ColumnScratch cols{};
         const vxp_status s = column_scratch(ctx, n, &cols);
         if (s != VXP_OK) return s;
@@ -516,7 +524,7 @@ vxp_status vxp_terrain_mesh_fused(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
     }
     ctx->chain_open = false;
     VXP_CUDA(ctx, vxp::launch_terrain_mesh(d_coords, n, seed, mode == VXP_MODE_GREEDY, *out, cols, ctx->stream));
-    ctx->launches += n ? 1 : 0;
+    ctx->launches += n ? 4 : 0;          // columns, heights, classification, mesh
     return VXP_OK;
 }
 
@@ -671,6 +679,7 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
             if (nbr6[i] < -1 || nbr6[i] >= (int64_t)n_stored) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     vxp_status s;
+    ctx->world_valid = false;            // the resident world is being replaced: valid again only when this call has succeeded
     if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n_stored, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_nbr6, &ctx->nbr_cap, n, 6)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_meta, &ctx->meta_cap, n, 1)) != VXP_OK) return s;
@@ -679,10 +688,6 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
     if ((s = grow_host_quads(ctx, ctx->quads_cap)) != VXP_OK) return s;
     const int32_t* d_nbr = nbr6 ? ctx->d_nbr6 : nullptr;
     const int greedy = mode == VXP_MODE_GREEDY;
-    ctx->world_n = n;                    // the world stays resident for vxp_remesh_edits_host
-    ctx->world_stored = n_stored;
-    ctx->world_has_nbr = nbr6 != nullptr;
-    ctx->world_valid = n > 0;
     const size_t chunk_bytes = (size_t)VXP_CHUNK_VOXELS * sizeof(uint16_t);
     uint64_t total = 0;
     bool done = false;
@@ -761,19 +766,28 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
             if ((s = grow_quads(ctx, total)) != VXP_OK) return s;
         }
     }
+    auto resident = [&] {                // the world stays on the device for vxp_remesh_edits_host
+        ctx->world_n = n;
+        ctx->world_stored = n_stored;
+        ctx->world_has_nbr = nbr6 != nullptr;
+        ctx->world_valid = n > 0;
+    };
     if (done || n == 0) {
         out->verts = ctx->h_verts;
         out->indices = ctx->h_indices;
         out->meta = ctx->h_meta;
         out->total_quads = total;
+        resident();
         return VXP_OK;
     }
-    return mesh_into_host(
+    s = mesh_into_host(
         ctx, n,
         [&](const vxp_mesh_dev& dev) {
             return chained_mesh_launch(ctx, ctx->d_voxels, d_nbr, n, greedy, dev) == VXP_OK ? cudaSuccess : cudaErrorUnknown;
         },
         out);
+    if (s == VXP_OK) resident();
+    return s;
 }
 
 vxp_status vxp_terrain_mesh_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t n, uint64_t seed,
@@ -790,7 +804,7 @@ vxp_status vxp_terrain_mesh_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
         [&](const vxp_mesh_dev& dev) {
             vxp::ColumnScratch cols{};
             if (n && column_scratch(ctx, n, &cols) != VXP_OK) return cudaErrorMemoryAllocation;
-            ctx->launches += n ? 1 : 0;
+            ctx->launches += n ? 4 : 0;
             return vxp::launch_terrain_mesh(ctx->d_coords, n, seed, mode == VXP_MODE_GREEDY, dev, cols, ctx->stream);
         },
         out);
@@ -819,16 +833,13 @@ vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t pa
             if (nbr6[i] < -1 || nbr6[i] >= (int64_t)n_stored) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     vxp_status s;
+    ctx->world_valid = false;            // valid again only when this call has succeeded
     if ((s = grow_device(ctx, &ctx->d_voxels, &ctx->voxels_cap, n_stored, VXP_CHUNK_VOXELS)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_nbr6, &ctx->nbr_cap, n, 6)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_packed, &ctx->packed_cap, (size_t)packed_bytes + 16, 1)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_offsets, &ctx->offsets_cap, n_stored, 1)) != VXP_OK) return s;
     if ((s = join_chain(ctx)) != VXP_OK) return s;
     if (ctx->status_pending && (s = vxp_ctx_synchronize(ctx)) != VXP_OK) return s;   // an earlier vxp_unpack_chunks verdict is not lost
-    ctx->world_n = n;
-    ctx->world_stored = n_stored;
-    ctx->world_has_nbr = nbr6 != nullptr;
-    ctx->world_valid = n > 0;
     const int32_t* d_nbr = nbr6 ? ctx->d_nbr6 : nullptr;
     if (n_stored) {
         VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_packed, packed, packed_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -838,12 +849,19 @@ vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t pa
         ctx->launches += 1;
     }
     const int greedy = mode == VXP_MODE_GREEDY;
-    return mesh_into_host(
+    s = mesh_into_host(
         ctx, n,
         [&](const vxp_mesh_dev& dev) {
             return chained_mesh_launch(ctx, ctx->d_voxels, d_nbr, n, greedy, dev) == VXP_OK ? cudaSuccess : cudaErrorUnknown;
         },
         out);
+    if (s == VXP_OK) {
+        ctx->world_n = n;
+        ctx->world_stored = n_stored;
+        ctx->world_has_nbr = nbr6 != nullptr;
+        ctx->world_valid = n > 0;
+    }
+    return s;
 }
 
 // Edits go up (12 bytes each), the voxels are patched and the dirty chunks re-meshed on the device, and only the

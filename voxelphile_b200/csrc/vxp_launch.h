@@ -5,7 +5,7 @@
 #include "../../include/vxp.h"
 
 namespace vxp {
-// Context-owned scratch of the mesh kernel (vxp_mesh4.cuh, "halo"): per meshed chunk one tag word and
+// Context-owned scratch of the mesh kernel (vxp_mesh_common.cuh, "halo"): per meshed chunk one tag word and
 // two 32-word x-boundary bit planes stored as epoch-stamped 64-bit words.  Both areas must be zero-filled
 // when allocated; epoch is a per-context launch counter in [1, 2^30) (the areas are re-zeroed when it
 // wraps).  tags == nullptr disables the exchange.
@@ -20,8 +20,12 @@ size_t boundary_plane_bytes(uint32_t n);
 // Context-owned scratch of the fused terrain+mesh path: the chunks of a batch that share a column (cx,cz)
 // share one height footprint.  Sized for a batch of n chunks: keys / id_of_slot have column_table_slots(n)
 // entries (a power of two, mask = slots - 1), slot_of_chunk has 2n (the second half is the work list of
-// chunks that cross the surface), coord_of_id n, heights n records of column_record_bytes(), count 3 words
-// (columns, work items, ticket).  Nothing needs initialising by the owner.
+// chunks that cross the surface), coord_of_id n, heights n records of column_record_bytes(), count
+// kColumnCounterWords words (columns, work items, ticket, CTAs done, 64-bit quad counter; 8-byte aligned).
+// keys and count must be zero-filled when allocated.  keys are stamped with `epoch` (in [1, 1023], advanced by
+// the owner per call; the owner re-zeroes keys when it wraps), so no call starts with a memset; the fused mesh
+// kernel leaves count zeroed.
+constexpr int kColumnCounterWords = 8;
 struct ColumnScratch {
     unsigned long long* keys;
     uint32_t* id_of_slot;
@@ -30,6 +34,7 @@ struct ColumnScratch {
     short* heights;
     uint32_t* count;
     uint32_t mask;
+    uint32_t epoch;
 };
 size_t column_table_slots(uint32_t n);
 size_t column_record_bytes();
@@ -43,7 +48,7 @@ cudaError_t launch_terrain_fill_columns(const vxp_coord* d_coords, uint32_t n, u
                                         const ColumnScratch& columns, cudaStream_t stream);
 cudaError_t launch_pattern_fill(const vxp_coord* d_coords, uint32_t n, int pattern, uint16_t* d_voxels,
                                 cudaStream_t stream);
-// One whole-batch launch.  `counter` is a context-owned, zero-initialised 8-byte launch counter (vxp_mesh4.cuh,
+// One whole-batch launch.  `counter` is a context-owned, zero-initialised 8-byte launch counter (vxp_mesh_common.cuh,
 // "launch chaining"): the kernel reserves quad ranges from it, hands the total to *out.total_quads and leaves it
 // zeroed, so no memset precedes the kernel.  overlap != 0 launches with programmatic stream serialisation: the
 // kernel may start while the previous mesh launch on the stream is still draining.  The caller must then alternate

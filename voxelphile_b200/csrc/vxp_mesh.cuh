@@ -1,28 +1,45 @@
-// vxp_mesh5.cuh — greedy meshing of stored chunks, generation 5: four CTAs per SM.
+// vxp_mesh.cuh — the two meshing kernels for stored chunks (SPEC §2-§5): one CTA (256 threads) per chunk.
 //
-// Generation 4 (vxp_mesh4.cuh) keeps the whole 64 KiB tile in shared memory, which caps an SM at three
-// chunks in flight; measured on config 3, two CTAs per SM take 96.7 us per batch and three 75.4 us, so the
-// kernel still gains from every chunk it can keep resident.  Nothing in the greedy pipeline needs the tile
-// once the occupancy and the id planes are out, so here the chunk is STREAMED through a ring of two 16 KiB
-// slabs (bulk TMA copies, two in flight, the next one issued as soon as a buffer has been converted) and the
-// post-tile arrays are cut to what fits the ring:
+// The chunk is STREAMED through a ring of 16 KiB slabs (bulk TMA copies, the next one issued as soon as a buffer
+// has been converted); nothing needs the voxels once the occupancy bits and the id bit planes are out, so what a
+// CTA keeps is small and several CTAs share an SM (greedy: four, culled: five):
 //
-//   ring (32 KiB)  ->  X-plane face masks, transposed equality rows of the X planes, staging / sweep log
-//   eq   (12.4 KiB)    id planes (kept in registers while streaming, stored for the chunks that use them);
+//   ring           ->  greedy: X-plane face masks, transposed equality rows of the X planes, staging / sweep log
+//                      culled: window of non-empty face words, staging
+//   eq   (12.4 KiB)    greedy: id planes (registers while streaming, stored for the chunks that use them);
 //                      the equality rows EX / EY / EZ afterwards (in place)
 //   occ  (4.5 KiB)     occupancy with halo; the Y / Z plane face masks are derived from it on the fly
 //                      (M = occ & ~occ_neighbour: two loads instead of one stored word)
 //
-// = 53.6 KiB per CTA.  Chunks whose ids do not fit the id planes stream a second time (L2 hits) and compute
-// their equality rows per voxel, slab by slab.  Everything else - halo exchange, bit-parallel row sweep with
-// its log, staging, flush, launch chaining - is generation 4's, reused from vxp_mesh4.cuh.
+// Greedy chunks whose ids do not fit the id planes stream a second time (L2 hits) and compute their equality
+// rows per voxel, slab by slab.  Halo exchange, quad-record store and launch chaining: vxp_mesh_common.cuh.
+//
+// Greedy sweep (SPEC §4 evaluated bit-parallel over the 32 columns of a plane).  After row v-1 every set cell of
+// that row belongs to exactly one active run (S = start bits, E = end bits, cover C = mask row v-1).  Row v: a
+// run survives iff all its cells are set in row v with the id of the cell above (X = C & M & V); survivors are
+// found with one carry chain upwards (segmented AND-reduce: T = (X & ~E) + S, Es = T & E & X) and spread back over
+// their run with one carry chain on the bit-reversed words.  Runs that do not survive are finished quads; the
+// cells of row v not covered by survivors start new runs, split where the id changes (H).
 #pragma once
-#include "vxp_mesh4.cuh"
+#include "vxp_mesh_common.cuh"
 
 namespace vxp {
-namespace v5 {
+namespace mesh {
 
-using namespace v4;
+// CTAs per SM the kernels are compiled for (and the fused path sizes its persistent grid with)
+#ifndef VXP_GREEDY_CTAS
+#define VXP_GREEDY_CTAS 4
+#endif
+#ifndef VXP_CULLED_CTAS
+#define VXP_CULLED_CTAS 5
+#endif
+constexpr int kGreedyCtas = VXP_GREEDY_CTAS, kCulledCtas = VXP_CULLED_CTAS;
+// what a chunk keeps besides the pipeline's own arrays: the carried layer of the second streaming pass (greedy, stored
+// chunks with large ids) or the column's height footprint (fused terrain path) - never both
+union Aux {
+    uint4 carry[128];
+    short heights[34 * 34 + 4];
+};
 
 struct PostG {   // what lives in the ring once the chunk has been streamed
     static constexpr int kCap = (2 * kSlabBytes - (64 * kPad + 2 * kPlaneWords) * 4) / 4;   // 3968 words
@@ -38,7 +55,7 @@ struct __align__(128) SmemG {
     } tile;
     uint32_t eq[3][kPlaneWords];   // [b][z*33+y]: id plane b while streaming; afterwards EX / EY / EZ (same layout as v4's ex / ey / ez)
     uint32_t occ[34 * 34];
-    uint4 carry[128];              // second streaming pass: the last layer of the previous slab
+    Aux aux;                       // second streaming pass: the last layer of the previous slab / fused path: heights
     uint32_t xh[2][32];
     uint32_t actz[32];
     uint32_t scratch[kWarps + 1];
@@ -54,7 +71,8 @@ struct __align__(128) SmemG {
     unsigned long long mbar[2];
 };
 static_assert(sizeof(PostG) <= 2 * kSlabBytes, "post layout overflows the ring");
-static_assert(4 * (sizeof(SmemG) + 1024) <= 227 * 1024 + 1024, "four CTAs per SM need <= 56 KiB each");
+// per CTA: the struct + 128 bytes of static shared memory (fused kernel) + 1 KiB the driver reserves; 227 KiB per SM
+static_assert(kGreedyCtas * (sizeof(SmemG) + 128 + 1024) <= 227 * 1024, "shared memory of the greedy kernels exceeds the CTAs-per-SM target");
 
 // ------------------------------------------------------------------ streaming
 __device__ __forceinline__ void issue_ring_slab(SmemG& sm, const uint16_t* gvox, int s) {
@@ -82,7 +100,7 @@ __device__ __forceinline__ void convert_ring_slab(SmemG& sm, int s, uint32_t& v_
     const uint32_t id = slab_or & 0xFFFFu;
     const uint32_t first = __shfl_sync(kFull, slab_or, 0);
     const bool same = slab_or == slab_and && id == (slab_or >> 16) && slab_or == first;
-    const bool uniform = __all_sync(kFull, same);              // the warp's 8 x 4 rows hold one value (v4::convert_rows)
+    const bool uniform = __all_sync(kFull, same);              // the warp's 8 x 4 rows hold one value: nothing to gather bit by bit
     uint32_t p0 = 0, p1 = 0, p2 = 0, ob = 0;
     if (uniform) {
         ob = id ? kFull : 0u;
@@ -141,7 +159,7 @@ __device__ __forceinline__ ChunkFlags reduce_flags_g(SmemG& sm, uint32_t v_or, u
 }
 
 // Second pass for chunks whose ids do not fit the planes: stream the chunk again and compute EX / EY / EZ of the
-// rows that carry a visible face from the voxels themselves (v4::equality_to_regs, slab by slab; the layer below a
+// rows that carry a visible face from the voxels themselves (slab by slab; the layer below a
 // slab's first one comes from sm.carry).  `phase` = number of completed phases of each ring barrier so far (2).
 __device__ __forceinline__ void equality_second_pass(SmemG& sm, const uint16_t* gvox) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -167,7 +185,7 @@ __device__ __forceinline__ void equality_second_pass(SmemG& sm, const uint16_t* 
             uint32_t w = (~nz8(xor4(q, px))) & 0xFFu;
             if (y > 0) w |= ((~nz8(xor4(q, slab[idx - 4]))) & 0xFFu) << 8;
             if (z > 0) {
-                const uint4 below = (z & 7) ? slab[idx - 128] : sm.carry[idx & 127];
+                const uint4 below = (z & 7) ? slab[idx - 128] : sm.aux.carry[idx & 127];
                 w |= ((~nz8(xor4(q, below))) & 0xFFu) << 16;
             }
             uint32_t t = __shfl_xor_sync(kFull, w, 1);
@@ -178,7 +196,7 @@ __device__ __forceinline__ void equality_second_pass(SmemG& sm, const uint16_t* 
         }
         __syncthreads();                                         // everybody has read the carried layer and this slab
         if (s + 1 < kSlabs) {
-            if (tid < 128) sm.carry[tid] = slab[7 * 128 + tid];  // layer 8s+7 for the first layer of slab s+1
+            if (tid < 128) sm.aux.carry[tid] = slab[7 * 128 + tid];  // layer 8s+7 for the first layer of slab s+1
             __syncthreads();
             if (tid == 0 && s + 2 < kSlabs) issue_ring_slab(sm, gvox, s + 2);
         }
@@ -437,7 +455,7 @@ __device__ __forceinline__ void stage_births_g(const SmemG& sm, bool with_eq, co
     }
 }
 
-// ------------------------------------------------------------------ masks -> quads -> buffers (v4::emit_chunk, greedy branch)
+// ------------------------------------------------------------------ masks -> quads -> buffers
 template <class IdFn>
 __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq, const MeshOut& out, IdFn id_of, Prof& prof) {
     const int tid = threadIdx.x;
@@ -471,7 +489,13 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
     unsigned long long f = 0;
     if (log_fits) {
         uint32_t births = 0;
+#ifdef VXP_PROFILE
+        const long long t_sw = clock64();
+#endif
         if (tid < 192) births = sweep_log_g(st, rm, (uint32_t)tid, log.entry + seg);
+#ifdef VXP_PROFILE
+        if (lane == 0 && blockIdx.x < kProfCtas) g_prof_warp[blockIdx.x][warp] = (unsigned int)(clock64() - t_sw);
+#endif
         // ordinal of every plane's first run: block-wide exclusive scan of the births, with one barrier (the log
         // is published by it too; sm.scratch is not written again before the chunk ends)
         const uint32_t incl = warp_incl_scan(births, lane);
@@ -628,8 +652,10 @@ __device__ __forceinline__ void mesh_chunk_g(SmemG& sm, const uint16_t* __restri
     emit_greedy(sm, mi, with_eq, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
 }
 
-// Same contract and launch chaining as v4::mesh_kernel<true>.
-__global__ void __launch_bounds__(kThreads, 4)
+// Meshes chunks [chunk0, hi) of a batch of n, one chunk per CTA (grid = hi - chunk0): the hardware block scheduler
+// is the load balancer.  (Persistent CTAs drawing tickets were measured 7-12 % slower: a CTA that draws its next
+// chunk early delays that chunk's boundary planes for the neighbours that poll them.)  Launch chaining: Chain.
+__global__ void __launch_bounds__(kThreads, kGreedyCtas)
 mesh_kernel_g(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, uint32_t chunk0, uint32_t hi,
               MeshOut out, Bnd bnd, Chain chain) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -658,7 +684,13 @@ mesh_kernel_g(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
         mi = blockIdx.x;
         active = active && chunk < n;
     }
+#ifdef VXP_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][0] = prof_now();
+#endif
     if (active) mesh_chunk_g(sm, voxels, nbr6, n, chunk, mi, out, bnd);
+#ifdef VXP_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][1] = prof_now();
+#endif
     if (threadIdx.x == 0 && chain.user_total != nullptr) {
         if (!sm.counted) red_add_u64(out.total, kCtaOne);
         if (closer) {
@@ -671,9 +703,9 @@ mesh_kernel_g(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
 }
 
 // ====================================================================== culled meshing, streamed: five CTAs per SM
-// The culled kernel never needed the ids of the tile either (block ids are gathered from the chunk in L2 when the
-// quads are written), so it streams the chunk through the same two-slab ring and keeps only the occupancy.  What
-// replaces generation 4's 48 KiB face-word list is a window of 2048 words (a terrain surface chunk has ~1500 non-
+// The culled kernel needs no ids at all while it scans (block ids are gathered from the chunk in L2 when the
+// quads are written), so it streams the chunk through the same two-slab ring and keeps only the occupancy.  The
+// non-empty face words are listed in a window of 2048 words (a terrain surface chunk has ~1500 non-
 // empty face words; a chunk with more is listed and flushed window by window) next to the 4096-record staging area:
 // 32 KiB in the ring + occupancy = 37.6 KiB per CTA.
 struct PostC {
@@ -688,6 +720,7 @@ struct __align__(128) SmemC {
         PostC post;
     } tile;
     uint32_t occ[34 * 34];
+    Aux aux;                       // fused path: heights
     uint32_t xh[2][32];
     uint32_t scratch[kWarps + 1];
     uint32_t cursor;
@@ -696,7 +729,7 @@ struct __align__(128) SmemC {
     unsigned long long mbar[2];
 };
 static_assert(sizeof(PostC) <= 2 * kSlabBytes, "post layout overflows the ring");
-static_assert(5 * (sizeof(SmemC) + 1024) <= 227 * 1024 + 1024, "five CTAs per SM need <= 45 KiB each");
+static_assert(kCulledCtas * (sizeof(SmemC) + 128 + 1024) <= 227 * 1024, "shared memory of the culled kernels exceeds the CTAs-per-SM target");
 
 __device__ __forceinline__ void issue_ring_slab_c(SmemC& sm, const uint16_t* gvox, int s) {
     mbar_expect_tx(&sm.mbar[s & 1], kSlabBytes);
@@ -740,7 +773,9 @@ __device__ __forceinline__ void convert_ring_slab_c(SmemC& sm, int s, uint32_t& 
     }
 }
 
-// v4::culled_emit with the word list cut into windows of PostC::kWordCap words.
+// One packed block scan gives every thread its first ordinal and its slot in the word list; the non-empty words are
+// listed (window by window, PostC::kWordCap words at a time) with the ordinal of their first quad; the threads
+// share the list evenly when they stage the quad records.
 template <class IdFn>
 __device__ __forceinline__ void culled_emit_c(SmemC& sm, uint32_t mi, uint32_t packed, const MeshOut& out, IdFn id_of, Prof& prof) {
     const int tid = threadIdx.x;
@@ -880,13 +915,10 @@ __device__ __forceinline__ void mesh_chunk_c(SmemC& sm, const uint16_t* __restri
     culled_emit_c(sm, mi, culled_count<false>(sm) + culled_count<true>(sm), out, id_of, prof);
 }
 
-// Same contract and launch chaining as v4::mesh_kernel<false>.
-// CTAs per SM the kernel is compiled for (measured on config 2: 3 = generation 4: 69.5 us; 4: 65.4 us at 61 registers;
+// Same contract and launch chaining as mesh_kernel_g.
+// CTAs per SM the kernel is compiled for (measured on config 2: 3 with a whole-tile layout: 69.5 us; 4: 65.4 us at 61 registers;
 // 5: 62.4 us at 48 registers, no spills; the shared memory would allow six, the registers would not)
-#ifndef VXP_CULLED_CTAS
-#define VXP_CULLED_CTAS 5
-#endif
-__global__ void __launch_bounds__(kThreads, VXP_CULLED_CTAS)
+__global__ void __launch_bounds__(kThreads, kCulledCtas)
 mesh_kernel_c(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ nbr6, uint32_t n, uint32_t chunk0, uint32_t hi,
               MeshOut out, Bnd bnd, Chain chain) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -913,7 +945,13 @@ mesh_kernel_c(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
         mi = blockIdx.x;
         active = active && chunk < n;
     }
+#ifdef VXP_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][0] = prof_now();
+#endif
     if (active) mesh_chunk_c(sm, voxels, nbr6, n, chunk, mi, out, bnd);
+#ifdef VXP_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x < kProfCtas) g_prof_time[blockIdx.x][1] = prof_now();
+#endif
     if (threadIdx.x == 0 && chain.user_total != nullptr) {
         if (!sm.counted) red_add_u64(out.total, kCtaOne);
         if (closer) {
@@ -925,5 +963,5 @@ mesh_kernel_c(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
     }
 }
 
-} // namespace v5
+} // namespace mesh
 } // namespace vxp

@@ -98,7 +98,14 @@ class HostMesh:
 
 
 class Mesher:
-    """One context = one GPU = one stream.  Mirrors ``vxp_ctx`` 1:1."""
+    """One context = one GPU.  Mirrors ``vxp_ctx`` 1:1.
+
+    Streams.  The device-level methods take and return torch tensors, so by default every call runs on torch's
+    CURRENT stream of the device (looked up per call): allocations, fills, kernels and read-backs are then ordered
+    the way torch orders its own work, and the caching allocator never recycles a block a kernel still uses.
+    ``use_stream(s)`` pins one stream instead; ``use_stream(None)`` selects the context's private non-blocking
+    stream, which has no ordering with torch's streams - only for callers that pass raw host pointers (the
+    host-level methods synchronise themselves) or that order device tensors with events of their own."""
 
     def __init__(self, device: int = 0):
         self._lib = _lib.load()
@@ -108,6 +115,8 @@ class Mesher:
         if st != _lib.VXP_OK:
             raise MeshError(st, self._lib.vxp_status_str(st).decode())
         self._h = h
+        self._follow = True          # run on torch's current stream, re-read at every device-level call
+        self._stream_ptr = None      # what the context was last told (None: its own stream)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -136,15 +145,28 @@ class Mesher:
         self._check(self._lib.vxp_ctx_set_overlap(self._h, 1 if enabled else 0))
 
     def use_stream(self, stream: Optional["torch.cuda.Stream"]):
-        """Run on a torch stream; ``None`` returns to the context's own non-blocking stream."""
+        """Pin a torch stream; ``None`` selects the context's own non-blocking stream (see the class docstring)."""
+        self._follow = False
         if stream is None:
             self._check(self._lib.vxp_ctx_reset_stream(self._h))
+            self._stream_ptr = None
         else:
             self._check(self._lib.vxp_ctx_set_stream(self._h, stream.cuda_stream or None))
+            self._stream_ptr = stream.cuda_stream
 
     def use_current_torch_stream(self):
+        """Back to the default: every device-level call runs on torch's current stream at the time of the call."""
+        self._follow = True
+        self._on_torch_stream()
+
+    def _on_torch_stream(self):
+        if not self._follow:
+            return
         import torch
-        self.use_stream(torch.cuda.current_stream(self.device))
+        ptr = torch.cuda.current_stream(self.device).cuda_stream
+        if ptr != self._stream_ptr:
+            self._check(self._lib.vxp_ctx_set_stream(self._h, ptr or None))
+            self._stream_ptr = ptr
 
     def synchronize(self):
         self._check(self._lib.vxp_ctx_synchronize(self._h))
@@ -155,6 +177,7 @@ class Mesher:
         return torch.device("cuda", self.device)
 
     def alloc_mesh(self, n: int, capacity: int) -> DeviceMesh:
+        self._on_torch_stream()
         import torch
         d = self._dev()
         return DeviceMesh(
@@ -172,6 +195,7 @@ class Mesher:
 
     def terrain_fill(self, coords: "torch.Tensor", seed: int, out: Optional["torch.Tensor"] = None):
         """coords: int32 [n,3] on this device -> int16 [n,32768] (u16 bit patterns)."""
+        self._on_torch_stream()
         import torch
         n = coords.shape[0]
         assert coords.dtype == torch.int32 and coords.is_contiguous() and coords.is_cuda
@@ -182,6 +206,7 @@ class Mesher:
         return out
 
     def pattern_fill(self, coords: "torch.Tensor", pattern: int, out: Optional["torch.Tensor"] = None):
+        self._on_torch_stream()
         import torch
         n = coords.shape[0]
         assert coords.dtype == torch.int32 and coords.is_contiguous() and coords.is_cuda
@@ -195,6 +220,7 @@ class Mesher:
              n_mesh: Optional[int] = None) -> DeviceMesh:
         """voxels: 16-bit [n_stored,32768] device tensor; nbr6: int32 [n,6] or None. Asynchronous.
         Only the first ``n_mesh`` (default all) chunks are meshed; the rest are read-only halo chunks."""
+        self._on_torch_stream()
         n = voxels.shape[0] if n_mesh is None else n_mesh
         assert voxels.is_cuda and voxels.is_contiguous() and voxels.element_size() == 2
         if nbr6 is not None:
@@ -208,6 +234,7 @@ class Mesher:
 
     def terrain_mesh(self, coords: "torch.Tensor", seed: int, mode: int, out: Optional[DeviceMesh] = None,
                      capacity: Optional[int] = None) -> DeviceMesh:
+        self._on_torch_stream()
         n = coords.shape[0]
         if out is None:
             out = self.alloc_mesh(n, capacity if capacity is not None else n * 256)
@@ -221,6 +248,7 @@ class Mesher:
                   out: Optional[DeviceMesh] = None, capacity: Optional[int] = None) -> DeviceMesh:
         """vxp_mesh_list: mesh the chunks named by ``chunk_list`` (int32/uint32 device tensor); meta entry k
         belongs to chunk chunk_list[k]."""
+        self._on_torch_stream()
         n, count = voxels.shape[0], int(chunk_list.shape[0])
         assert chunk_list.is_cuda and chunk_list.is_contiguous() and chunk_list.element_size() == 4
         if out is None:
@@ -235,6 +263,7 @@ class Mesher:
         """vxp_remesh_edits: apply ``edits`` (device tensor of EDIT_DTYPE records viewed as int32 [m,3]) to
         ``voxels`` in place and re-mesh the invalidated chunks.  Returns (dirty list tensor, count tensor, DeviceMesh);
         nothing is synchronised."""
+        self._on_torch_stream()
         import torch
         n, m = voxels.shape[0], int(edits.shape[0])
         cap = min(n, 7 * m)
@@ -266,6 +295,7 @@ class Mesher:
     # ------------------------------------------------------------ chunk wire format (SPEC §10)
     def pack(self, voxels: "torch.Tensor", capacity_bytes: Optional[int] = None):
         """vxp_pack_chunks: (packed uint8 tensor, offsets int64 tensor [n], total-bytes int64 tensor [1]); async."""
+        self._on_torch_stream()
         import torch
         n = voxels.shape[0]
         cap = n * (48 + 65536) if capacity_bytes is None else capacity_bytes
@@ -278,6 +308,7 @@ class Mesher:
 
     def unpack(self, packed: "torch.Tensor", offsets: "torch.Tensor", out: Optional["torch.Tensor"] = None) -> "torch.Tensor":
         """vxp_unpack_chunks: int16 [n, 32768]; a malformed record surfaces at the next synchronize()."""
+        self._on_torch_stream()
         import torch
         n = int(offsets.shape[0])
         if out is None:
@@ -311,6 +342,7 @@ class Mesher:
     # ------------------------------------------------------------ level of detail (SPEC §11)
     def downsample(self, voxels: "torch.Tensor", child8: "torch.Tensor", out: Optional["torch.Tensor"] = None) -> "torch.Tensor":
         """vxp_downsample_chunks: child8 int32 [n_out, 8] (dx + 2 dy + 4 dz, -1 = air) -> int16 [n_out, 32768]."""
+        self._on_torch_stream()
         import torch
         n_out = int(child8.shape[0])
         assert child8.is_cuda and child8.is_contiguous() and child8.shape[1] == 8
