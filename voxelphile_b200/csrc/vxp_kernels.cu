@@ -305,7 +305,7 @@ __device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemG& sm, const vxp_co
     mesh::emit_greedy(sm, chunk, with_eq, out, [s_h, Y0](int idx) -> uint32_t {
         const int x = idx & 31, y = (idx >> 5) & 31, z = idx >> 10;
         return terrain_block(s_h[(z + 1) * 34 + x + 1], Y0 + y);
-    }, [] {}, prof);
+    }, prof);
 }
 __device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemC& sm, const vxp_coord* __restrict__ coords,
                                                    const ColumnScratch& cs, uint32_t chunk, const mesh::MeshOut& out) {

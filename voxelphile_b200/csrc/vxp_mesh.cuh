@@ -216,10 +216,9 @@ __device__ __forceinline__ uint32_t build_masks_g(SmemG& sm, bool with_eq, bool 
         const int z = k * kWarps + warp, y = lane;
         const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
         const uint32_t c = o[0];
-        // the x halo is NOT applied here: it only matters to the planes (f=0, x=0) and (f=1, x=31), whose mask rows
-        // get it from sm.xh when they are read (mask_rows) - so the masks do not wait for the x neighbours' planes
-        tx[k] = c & ~(c << 1);                          // -X visible, bit x (bit 0: as if the halo were air)
-        tx[4 + k] = c & ~(c >> 1);                      // +X visible, bit x (bit 31: likewise)
+        const uint32_t lo = (sm.xh[0][z] >> y) & 1u, hi = (sm.xh[1][z] >> y) & 1u;
+        tx[k] = c & ~((c << 1) | lo);                   // -X visible, bit x
+        tx[4 + k] = c & ~((c >> 1) | (hi << 31));       // +X visible, bit x
         const uint32_t my = c & ~o[-1], py = c & ~o[+1], mz = c & ~o[-34], pz = c & ~o[+34];
         acc |= my | py | mz | pz | tx[k] | tx[4 + k];
         // non-empty rows of the planes (what the sweep visits): Z planes (slice z, row y) by ballot, Y planes
@@ -289,9 +288,7 @@ __device__ __forceinline__ uint32_t build_masks_g(SmemG& sm, bool with_eq, bool 
 }
 
 // ------------------------------------------------------------------ face-mask rows
-// Row v of plane (f, s): stored for the X planes (minus the x halo for the two boundary planes), occ & ~occ_neighbour
-// for the others.  sm.rows (non-empty rows of a plane, from build_masks_g) is therefore a superset for the two
-// boundary planes (see emit_greedy).
+// Row v of plane (f, s): stored for the X planes, occ & ~occ_neighbour for the others.
 struct MaskRows {
     const uint32_t* c;   // centre word of row 0
     const uint32_t* nb;  // neighbour word of row 0 (&sm.zero for stored masks)
@@ -301,11 +298,7 @@ struct MaskRows {
 __device__ __forceinline__ MaskRows mask_rows(const SmemG& sm, uint32_t plane) {
     const uint32_t f = plane >> 5, s = plane & 31u;
     MaskRows m;
-    if (f < 2) {
-        m.c = sm.tile.post.xmask + plane * kPad; m.cs = 1; m.nb = &sm.zero; m.ns = 0;
-        if (plane == 0u) { m.nb = sm.xh[0]; m.ns = 1; }          // x = 0 of -X: row z, bit y against the -X halo
-        if (plane == 63u) { m.nb = sm.xh[1]; m.ns = 1; }         // x = 31 of +X
-    }
+    if (f < 2) { m.c = sm.tile.post.xmask + plane * kPad; m.cs = 1; m.nb = &sm.zero; m.ns = 0; }
     else if (f < 4) { m.c = sm.occ + 34 + (s + 1); m.cs = 34; m.nb = m.c + (f == 2 ? -1 : 1); m.ns = 34; }      // slice y = s, row z
     else { m.c = sm.occ + (s + 1) * 34 + 1; m.cs = 1; m.nb = m.c + (f == 4 ? -34 : 34); m.ns = 1; }             // slice z = s, row y
     return m;
@@ -320,12 +313,12 @@ struct SweepG {
     uint32_t C, S, E, r0, r1, r2, r3, r4;
     uint32_t base;
 };
-// plane < 0: the thread owns no plane (its state is never consulted)
-__device__ __forceinline__ void sweep_init_g(SweepG& st, SmemG& sm, bool with_eq, int plane) {
-    const int f = plane >= 0 ? plane >> 5 : 0, s = plane >= 0 ? plane & 31 : 0;
+__device__ __forceinline__ void sweep_init_g(SweepG& st, SmemG& sm, bool with_eq) {
+    const int tid = threadIdx.x;
+    const int f = tid >> 5, s = tid & 31;
     st.C = st.S = st.E = st.r0 = st.r1 = st.r2 = st.r3 = st.r4 = 0;
     st.base = (uint32_t)f << 15 | (uint32_t)s << 10;
-    st.m = mask_rows(sm, plane >= 0 ? (uint32_t)plane : 1u);
+    st.m = mask_rows(sm, tid < 192 ? (uint32_t)tid : 0u);
     st.hb = st.vb = &sm.ones;
     st.hs = st.vs = 0;
     if (with_eq) {
@@ -394,10 +387,7 @@ __device__ __forceinline__ uint32_t sweep_rows_g(const SweepG& st) {
     for (int v = 0; v < 32; ++v) rm |= (uint32_t)(st.m.row(v) != 0) << v;
     return rm;
 }
-// rm: the rows to visit and log.  kSparse (the two boundary planes): the plane's log segment has a slot for every row
-// of `slots` (a superset of rm: the rows collected before the x halo was known), and row v goes to its slot there.
-template <bool kSparse>
-__device__ __forceinline__ uint32_t sweep_log_g(SweepG& st, uint32_t rm, uint32_t slots, uint32_t plane, uint2* entry) {
+__device__ __forceinline__ uint32_t sweep_log_g(SweepG& st, uint32_t rm, uint32_t plane, uint2* entry) {
     uint32_t births = 0;
     uint32_t todo = rm | (rm << 1);
     const int trips = (int)__reduce_max_sync(kFull, (uint32_t)__popc(todo));
@@ -423,11 +413,7 @@ __device__ __forceinline__ uint32_t sweep_log_g(SweepG& st, uint32_t rm, uint32_
             st.S = (st.S & Cs) | NS;
             st.E = (st.E & Cs) | NE;
             st.C = Mv;
-            if (Mv) {
-                const uint2 en = make_uint2(Cs, plane << 5 | (uint32_t)v | births << 13);
-                if constexpr (kSparse) entry[__popc(slots & ((1u << v) - 1u))] = en;
-                else *entry++ = en;
-            }
+            if (Mv) *entry++ = make_uint2(Cs, plane << 5 | (uint32_t)v | births << 13);
             births += __popc(NS);
         }
         v = vn; valid = validn; Mv = Mn; Hv = Hn; Vv = Vn;
@@ -470,70 +456,43 @@ __device__ __forceinline__ void stage_births_g(const SmemG& sm, bool with_eq, co
 }
 
 // ------------------------------------------------------------------ masks -> quads -> buffers
-// Plane ownership in the sweep: thread t < 192 owns plane t - except the two boundary planes (f=0, x=0) and (f=1, x=31),
-// the only ones whose faces depend on the x halo.  They belong to lane 0 of warps 6 and 7, which first run x_halo()
-// (stored chunks: wait for the x neighbour's boundary plane, vxp_mesh_common.cuh; fused path: nothing to do) while
-// warps 0..5 are already sweeping.  sm.rows of those two planes was collected without the halo (a superset): their log
-// segments have a slot per superset row; rows the halo empties get an empty entry, the others are swept.
-template <class IdFn, class XFn>
-__device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq, const MeshOut& out, IdFn id_of, XFn x_halo, Prof& prof) {
+template <class IdFn>
+__device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq, const MeshOut& out, IdFn id_of, Prof& prof) {
     const int tid = threadIdx.x;
     constexpr uint32_t kCap = PostG::kCap;
     uint32_t* const staging = sm.tile.post.staging;
     auto nothing = [] {};
     auto staged = [staging](uint32_t i) { return staging[i]; };
     if (tid == 0) sm.cursor = 0;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int bplane = warp == 6 ? 0 : 63;              // warps 6, 7: the boundary plane of the warp
-    int plane = (tid < 192 && tid != 0 && tid != 63) ? tid : -1;
-    if (lane == 0 && warp >= 6) plane = bplane;
     SweepG st;
-    sweep_init_g(st, sm, with_eq, plane);
+    sweep_init_g(st, sm, with_eq);
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t rm = tid < 192 ? sm.rows[tid] : 0u;   // from build_masks_g
     // first log entry of every plane = exclusive prefix of the planes' non-empty rows.  Every warp adds up the six
     // faces for itself (six loads, six warp reductions): no barrier, where a block-wide scan needs two.
-    uint32_t nL = 0, seg = 0, tot01 = 0;
+    uint32_t nL = 0, seg = 0;
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
         const uint32_t tot = __reduce_add_sync(kFull, (uint32_t)__popc(sm.rows[f * 32 + lane]));
         nL += tot;
         if (f < warp) seg += tot;
-        if (f < 2) tot01 += tot;
     }
-    uint32_t rm = 0, slots = 0;
-    if (warp < 6) {
-        const uint32_t r = sm.rows[tid];
-        seg += warp_incl_scan((uint32_t)__popc(r), lane) - (uint32_t)__popc(r);
-        sm.seg[tid] = seg;                              // (threads 0 and 63 too: the segment of a plane does not depend on its owner)
-        if (plane >= 0) rm = slots = r;
-    }
+    seg += warp_incl_scan((uint32_t)__popc(rm), lane) - (uint32_t)__popc(rm);
+    if (tid < 192) sm.seg[tid] = seg;
     const bool log_fits = 2 * nL <= kCap;
     SweepLog log;
     log.entry = reinterpret_cast<uint2*>(staging + kCap - 2 * nL);
     log.seg = sm.seg;
     log.rows = sm.rows;
     log.first = sm.first_run;
-    uint2* my_entry = log.entry + seg;
-    if (warp >= 6) {
-        x_halo();                                       // sm.xh[warp - 6] complete (written by this warp, or long before)
-        __syncwarp();
-        const uint32_t sup = sm.rows[bplane];
-        const uint32_t exact = __ballot_sync(kFull, (sm.tile.post.xmask[bplane * kPad + lane] & ~sm.xh[warp - 6][lane]) != 0u);
-        my_entry = log.entry + (warp == 6 ? 0u : tot01 - (uint32_t)__popc(sup));
-        if (log_fits && ((sup & ~exact) >> lane) & 1u)
-            my_entry[__popc(sup & ((1u << lane) - 1u))] = make_uint2(0u, (uint32_t)bplane << 5 | (uint32_t)lane);
-        if (lane == 0) { rm = exact; slots = sup; }
-    }
     uint32_t Q = 0;
     unsigned long long f = 0;
-    auto with_height = [&log](uint32_t r) { return r | (run_height(log, r) - 1u) << 23; };
-    auto as_staged = [](uint32_t r) { return r; };
     if (log_fits) {
         uint32_t births = 0;
 #ifdef VXP_PROFILE
         const long long t_sw = clock64();
 #endif
-        if (warp < 6) births = sweep_log_g<false>(st, rm, slots, (uint32_t)plane, my_entry);
-        else births = sweep_log_g<true>(st, rm, slots, (uint32_t)bplane, my_entry);
+        if (tid < 192) births = sweep_log_g(st, rm, (uint32_t)tid, log.entry + seg);
 #ifdef VXP_PROFILE
         if (lane == 0 && blockIdx.x < kProfCtas) g_prof_warp[blockIdx.x][warp] = (unsigned int)(clock64() - t_sw);
 #endif
@@ -549,7 +508,7 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
             if (w < warp) first_run += t;
             Q += t;
         }
-        if (plane >= 0) sm.first_run[plane] = first_run;
+        if (tid < 192) sm.first_run[tid] = first_run;
         if (tid == 0) f = reserve_quads(sm, out, Q);
         prof.mark(5);
         // The records go below the log if they fit; otherwise - the sweep being over, its V rows are dead - the first
@@ -566,7 +525,7 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
             stage_births_g(sm, with_eq, log, nL, rec);
             __syncthreads();
             prof.mark(6);
-            flush_staging(sm, [rec](uint32_t i) { return rec.at(i); }, with_height,
+            flush_staging(sm, [rec, &log](uint32_t i) { const uint32_t r = rec.at(i); return r | (run_height(log, r) - 1u) << 23; },
                           Q, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, mi, Q, f, out); }, true);
             prof.mark(7);
             return;
@@ -581,9 +540,9 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
                 stage_births_g(sm, with_eq, log, nL, rec, lo, hi);
                 __syncthreads();
                 bool ok;
-                if (lo == 0) ok = flush_staging(sm, [rec](uint32_t i) { return rec.at(i); }, with_height,
+                if (lo == 0) ok = flush_staging(sm, [rec, &log](uint32_t i) { const uint32_t r = rec.at(i); return r | (run_height(log, r) - 1u) << 23; },
                                                 hi, 0, out, id_of, [&] { if (tid == 0) publish_range(sm, mi, Q, f, out); }, true);
-                else ok = flush_staging(sm, [rec](uint32_t i) { return rec.at(i); }, with_height,
+                else ok = flush_staging(sm, [rec, &log](uint32_t i) { const uint32_t r = rec.at(i); return r | (run_height(log, r) - 1u) << 23; },
                                         hi - lo, lo, out, id_of, nothing, false);
                 if (!ok) return;
             }
@@ -591,8 +550,8 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
             return;
         }
     } else {
-        __syncthreads();                              // cursor = 0 and the x halo published
-        if (plane >= 0) {
+        __syncthreads();                              // cursor = 0 published
+        if (tid < 192) {
 #pragma unroll 1
             for (int v = 0; v <= 32; ++v) sweep_step_g(st, v, staging, 0u, &sm.cursor);
         }
@@ -603,7 +562,7 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
     // heavy path (the log or the records do not fit): stepped sweep, half of the planes per step, flushing in rounds
     prof.count(14);
     if (tid == 0) publish_range(sm, mi, Q, f, out);
-    sweep_init_g(st, sm, with_eq, plane);
+    sweep_init_g(st, sm, with_eq);
     uint32_t flushed = 0;
     __syncthreads();                                  // everybody is done with the log before the cursor restarts
     if (tid == 0) sm.cursor = 0;
@@ -612,11 +571,11 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             __syncthreads();
-            if (plane >= 0 && (plane >= 96) == (half == 1)) sweep_step_g(st, v, staging, kCap, &sm.cursor);
+            if (tid < 192 && (tid >= 96) == (half == 1)) sweep_step_g(st, v, staging, kCap, &sm.cursor);
             __syncthreads();
             const uint32_t cnt = sm.cursor;
             if (cnt + 96 * 32 > kCap || (v == 32 && half == 1)) {
-                if (!flush_staging(sm, staged, as_staged, cnt, flushed, out, id_of, nothing, false)) return;
+                if (!flush_staging(sm, staged, cnt, flushed, out, id_of, nothing, false)) return;
                 flushed += cnt;
                 __syncthreads();
                 if (tid == 0) sm.cursor = 0;
@@ -637,9 +596,7 @@ __device__ __forceinline__ void mesh_chunk_g(SmemG& sm, const uint16_t* __restri
         issue_ring_slab(sm, gvox, 0);
         issue_ring_slab(sm, gvox, 1);
     }
-    // neighbour across the face this warp looks after: warps 2..5 the +-Y / +-Z halo rows, warps 6, 7 the -X / +X halo
-    const int xface = x_face<6>();
-    const int nb = (nbr6 && tid >= 64) ? __ldg(nbr6 + 6 * (size_t)chunk + (xface >= 0 ? xface : (tid >> 5))) : -1;
+    const int nb = (nbr6 && tid < 192) ? __ldg(nbr6 + 6 * (size_t)chunk + (tid >> 5)) : -1;
     HaloRows rows;
     issue_yz_halo(rows, voxels, nb);
 
@@ -665,35 +622,26 @@ __device__ __forceinline__ void mesh_chunk_g(SmemG& sm, const uint16_t* __restri
     }
     const bool with_eq = !fl.single_id;
     const bool with_planes = with_eq && fl.small_ids;
-    // The x halo only decides (a) whether an all-solid chunk is buried and (b) the faces of two of the 192 planes, so
-    // only an all-solid chunk waits for it here; everybody else hands the wait to warps 6, 7, which sit it out while
-    // warps 0..5 sweep (emit_greedy).
     XPoll xp;
-    x_poll_begin(xface, nb, n, bnd, xp);                // first read of the x neighbours' planes: in flight from here on
-    const bool air_yz = halo_begin(sm, nb, rows);       // +-Y / +-Z halo rows
-    if (with_planes) store_id_planes_g(sm, ip);
-    if (tid < 192) sm.rows[tid] = 0u;
-    const bool x_pending = !fl.all_solid;
-    if (!x_pending) {
-        const bool air_x = halo_finish(sm, voxels, xface, nb, n, bnd, xp, prof);
-        const bool halo_air = __syncthreads_or(air_yz || air_x);   // barrier: halo published
-        prof.mark(2);
-        if (!halo_air) {                                // buried: no faces
-            if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};
-            prof.count(9);
-            return;
-        }
-    } else {
-        __syncthreads();                                // +-Y / +-Z halo rows, id planes and the zeroed row masks published
-        prof.mark(2);
+    const bool air_yz = halo_begin(sm, nb, n, bnd, rows, xp);
+    if (with_planes) store_id_planes_g(sm, ip);         // while the x neighbours' boundary planes are on their way
+    const bool air_x = halo_finish(sm, voxels, nb, n, bnd, xp, prof);
+    const bool halo_air = __syncthreads_or(air_yz || air_x);   // barrier: halo (and id planes) published
+    prof.mark(2);
+    if (fl.all_solid && !halo_air) {
+        if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};
+        prof.count(9);
+        return;
     }
     if (with_eq && !with_planes) {
-        build_active(sm, x_pending);                    // (x halo still unknown: taken as air, a superset of the rows that matter)
+        build_active(sm);
         __syncthreads();
         equality_second_pass(sm, gvox);                 // ends with a barrier
     }
+    if (tid < 192) sm.rows[tid] = 0u;
+    __syncthreads();
     prof.mark(3);
-    const bool any = __syncthreads_or(build_masks_g(sm, with_eq, with_planes) != 0);   // barrier: masks and row masks published
+    const bool any = __syncthreads_or(build_masks_g(sm, with_eq, with_planes) != 0);
     prof.mark(4);
     if (!any) {
         if (tid == 0) out.meta[mi] = vxp_chunk_meta{0u, 0u};
@@ -701,8 +649,7 @@ __device__ __forceinline__ void mesh_chunk_g(SmemG& sm, const uint16_t* __restri
         return;
     }
     prof.count(11);
-    emit_greedy(sm, mi, with_eq, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); },
-                [&] { if (x_pending) halo_finish(sm, voxels, xface, nb, n, bnd, xp, prof); }, prof);
+    emit_greedy(sm, mi, with_eq, out, [gvox](int idx) -> uint32_t { return __ldg(gvox + idx); }, prof);
 }
 
 // Meshes chunks [chunk0, hi) of a batch of n, one chunk per CTA (grid = hi - chunk0): the hardware block scheduler
@@ -714,7 +661,8 @@ mesh_kernel_g(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemG& sm = *reinterpret_cast<SmemG*>(smem_raw);
     const bool dealt = chain.runs != 0u && (blockIdx.x >> 4) < chain.runs;
-    if (dealt && threadIdx.x == 0) sm.cursor = dealt_chunk(chain, chunk0, blockIdx.x);
+    if (dealt && threadIdx.x == 0)
+        sm.cursor = (uint32_t)(((unsigned long long)(blockIdx.x >> 4) * chain.run_stride) % chain.runs) * 16u + (blockIdx.x & 15u);
     const bool closer = chain.user_total != nullptr && blockIdx.x == gridDim.x - 1;
     if (threadIdx.x == 0) {
         if (closer) griddep_wait();
@@ -836,7 +784,6 @@ __device__ __forceinline__ void culled_emit_c(SmemC& sm, uint32_t mi, uint32_t p
     uint32_t* const staging = P.staging;
     auto nothing = [] {};
     auto staged = [staging](uint32_t i) { return staging[i]; };
-    auto as_staged = [](uint32_t r) { return r; };
     const int y = tid & 31, w = tid >> 5;
     uint32_t tot;
     const uint32_t pre = block_excl_scan(packed, sm.scratch, &tot);
@@ -897,8 +844,8 @@ __device__ __forceinline__ void culled_emit_c(SmemC& sm, uint32_t mi, uint32_t p
             __syncthreads();
             prof.mark(6);
             bool fits;
-            if (first_flush) fits = flush_staging(sm, staged, as_staged, end - base, base, out, id_of, [&] { if (tid == 0) publish_range(sm, mi, Q, fq, out); }, true);
-            else fits = flush_staging(sm, staged, as_staged, end - base, base, out, id_of, nothing, false);
+            if (first_flush) fits = flush_staging(sm, staged, end - base, base, out, id_of, [&] { if (tid == 0) publish_range(sm, mi, Q, fq, out); }, true);
+            else fits = flush_staging(sm, staged, end - base, base, out, id_of, nothing, false);
             first_flush = false;
             if (!fits) return;
             __syncthreads();
@@ -917,7 +864,6 @@ __device__ __forceinline__ void mesh_chunk_c(SmemC& sm, const uint16_t* __restri
         issue_ring_slab_c(sm, gvox, 0);
         issue_ring_slab_c(sm, gvox, 1);
     }
-    const int xface = x_face<0>();                      // warps 0, 1: the -X / +X halo; warps 2..5: the +-Y / +-Z halo rows
     const int nb = (nbr6 && tid < 192) ? __ldg(nbr6 + 6 * (size_t)chunk + (tid >> 5)) : -1;
     HaloRows rows;
     issue_yz_halo(rows, voxels, nb);
@@ -947,20 +893,18 @@ __device__ __forceinline__ void mesh_chunk_c(SmemC& sm, const uint16_t* __restri
     XPoll xp;
     if (!fl.all_solid) {
         // count the faces that do not depend on the x halo (+-Y, +-Z) while the x neighbours' boundary planes are on their way
-        x_poll_begin(xface, nb, n, bnd, xp);
-        halo_begin(sm, nb, rows);
+        halo_begin(sm, nb, n, bnd, rows, xp);
         __syncthreads();                                // +-Y / +-Z halo rows published
         uint32_t packed = culled_count<false>(sm);
-        halo_finish(sm, voxels, xface, nb, n, bnd, xp, prof);
+        halo_finish(sm, voxels, nb, n, bnd, xp, prof);
         __syncthreads();                                // x halo published
         prof.mark(2);
         packed += culled_count<true>(sm);
         culled_emit_c(sm, mi, packed, out, id_of, prof);
         return;
     }
-    x_poll_begin(xface, nb, n, bnd, xp);
-    const bool air_yz = halo_begin(sm, nb, rows);
-    const bool air_x = halo_finish(sm, voxels, xface, nb, n, bnd, xp, prof);
+    const bool air_yz = halo_begin(sm, nb, n, bnd, rows, xp);
+    const bool air_x = halo_finish(sm, voxels, nb, n, bnd, xp, prof);
     const bool halo_air = __syncthreads_or(air_yz || air_x);   // barrier: halo published
     prof.mark(2);
     if (!halo_air) {                                    // buried: no faces
@@ -980,7 +924,8 @@ mesh_kernel_c(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemC& sm = *reinterpret_cast<SmemC*>(smem_raw);
     const bool dealt = chain.runs != 0u && (blockIdx.x >> 4) < chain.runs;
-    if (dealt && threadIdx.x == 0) sm.cursor = dealt_chunk(chain, chunk0, blockIdx.x);
+    if (dealt && threadIdx.x == 0)
+        sm.cursor = (uint32_t)(((unsigned long long)(blockIdx.x >> 4) * chain.run_stride) % chain.runs) * 16u + (blockIdx.x & 15u);
     const bool closer = chain.user_total != nullptr && blockIdx.x == gridDim.x - 1;
     if (threadIdx.x == 0) {
         if (closer) griddep_wait();

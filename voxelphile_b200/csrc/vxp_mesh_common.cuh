@@ -178,62 +178,56 @@ __device__ __forceinline__ void publish_boundary(const SM& sm, const Bnd& bnd, u
     }
 }
 
-// Fill the halo of sm.occ / sm.xh.  The +-Y / +-Z faces (2..5) belong to warps 2..5 (halo_begin); the two x faces
-// belong to the warps kXWarp and kXWarp + 1 (culled: 0, 1; greedy: 6, 7, which have no part in the sweep and can sit
-// out the wait for their neighbour's plane while the other warps sweep):
-// x_poll_begin  issue the first read of the x neighbour's tag and boundary plane (two loads in flight together, not waited for)
-// halo_finish   use what came back, re-read a bounded number of times if the words were not there yet, and finally
-//               gather from the neighbour's voxels; writes sm.xh[face]
-// halo_begin / halo_finish return (per thread) whether any halo bit this thread produced is air.  No barriers inside.
+// Fill the halo of sm.occ / sm.xh: warp f < 6 produces the 32 words of face f.  Returns (per
+// thread) whether any halo bit this thread produced is air.  Contains no barrier.
+// nb = neighbour index of face f = warp index (loaded by the caller before the tile wait).
 #ifndef VXP_PLANE_POLLS
 #define VXP_PLANE_POLLS 8
 #endif
 constexpr int kPlanePolls = VXP_PLANE_POLLS;   // bounded re-reads of a boundary plane that is not there yet (never a wait-for);
                                                // measured on config 2: 1 -> 109.4 us, 3 -> 104.9, 6 -> 104.1, 12 -> 103.5
+// The halo is produced in two steps so that callers with something else to do can put it between them:
+// halo_begin   warps 2..5 write their +-Y / +-Z halo rows; warps 0,1 issue the first read of their x
+//              neighbour's tag and boundary plane (two loads in flight together, not waited for)
+// halo_finish  warps 0,1 use what came back, re-read a bounded number of times if the words were not there
+//              yet, and finally gather from the neighbour's voxels; they write sm.xh
+// Both return (per thread) whether any halo bit this thread produced is air.  Neither contains a barrier.
 struct XPoll {
     unsigned long long pw;
     uint32_t tag;
     bool armed;
 };
-// face of the x halo this thread's warp owns (0: -X, 1: +X), or -1
-template <int kXWarp>
-__device__ __forceinline__ int x_face() {
-    const int w = (int)(threadIdx.x >> 5) - kXWarp;
-    return (w == 0 || w == 1) ? w : -1;
-}
-__device__ __forceinline__ void x_poll_begin(int face, int nb, uint32_t n, const Bnd& bnd, XPoll& xp) {
-    const int lane = threadIdx.x & 31;
+template <class SM>
+__device__ __forceinline__ bool halo_begin(SM& sm, int nb, uint32_t n, const Bnd& bnd, const HaloRows& rows, XPoll& xp) {
+    const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
     xp.armed = false;
     xp.tag = 0;
     xp.pw = 0;
-    if (face >= 0 && nb >= 0 && bnd.tags && (uint32_t)nb < n) {
+    if (f >= 6) return false;
+    if (f >= 2) {
+        uint32_t word = 0;
+        if (nb >= 0) word = nz8(rows.q[0]) | nz8(rows.q[1]) << 8 | nz8(rows.q[2]) << 16 | nz8(rows.q[3]) << 24;
+        sm.occ[f == 2 ? (lane + 1) * 34 : f == 3 ? (lane + 1) * 34 + 33 : f == 4 ? lane + 1 : 33 * 34 + lane + 1] = word;
+        return word != kFull;
+    }
+    if (nb >= 0 && bnd.tags && (uint32_t)nb < n) {
         xp.tag = ld_relaxed_u32(bnd.tags + nb);
-        xp.pw = ld_relaxed_u64(bnd.planes + (size_t)nb * 64 + (face ^ 1) * 32 + lane);
+        xp.pw = ld_relaxed_u64(bnd.planes + (size_t)nb * 64 + (f ^ 1) * 32 + lane);
         xp.armed = true;
     }
+    return false;
 }
-// nb = neighbour across face (warp index) for warps 2..5
 template <class SM>
-__device__ __forceinline__ bool halo_begin(SM& sm, int nb, const HaloRows& rows) {
-    const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
-    if (f < 2 || f >= 6) return false;
-    uint32_t word = 0;
-    if (nb >= 0) word = nz8(rows.q[0]) | nz8(rows.q[1]) << 8 | nz8(rows.q[2]) << 16 | nz8(rows.q[3]) << 24;
-    sm.occ[f == 2 ? (lane + 1) * 34 : f == 3 ? (lane + 1) * 34 + 33 : f == 4 ? lane + 1 : 33 * 34 + lane + 1] = word;
-    return word != kFull;
-}
-// face / nb: the x face this warp owns (-1: none) and the neighbour across it
-template <class SM>
-__device__ __forceinline__ bool halo_finish(SM& sm, const uint16_t* __restrict__ voxels, int face, int nb, uint32_t n, const Bnd& bnd,
+__device__ __forceinline__ bool halo_finish(SM& sm, const uint16_t* __restrict__ voxels, int nb, uint32_t n, const Bnd& bnd,
                                             XPoll xp, Prof& prof) {
-    const int lane = threadIdx.x & 31;
-    if (face < 0) return false;
+    const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
+    if (f >= 2) return false;
     uint32_t word = 0;
     if (nb >= 0) {
         bool have = false;
         if (xp.armed) {
             const uint32_t* tagp = bnd.tags + nb;
-            const unsigned long long* planep = bnd.planes + (size_t)nb * 64 + (face ^ 1) * 32 + lane;
+            const unsigned long long* planep = bnd.planes + (size_t)nb * 64 + (f ^ 1) * 32 + lane;
             for (int t = 0;; ++t) {
                 if ((xp.tag >> 2) == bnd.epoch) {                       // all air / all solid neighbour
                     word = (xp.tag & 3u) == kTagSolid ? kFull : 0u;
@@ -250,7 +244,7 @@ __device__ __forceinline__ bool halo_finish(SM& sm, const uint16_t* __restrict__
             if (lane == 0) prof.count(have ? 12 : 13);
         }
         if (!have) {                                      // gather from the neighbour's voxels: one u16 per 64-byte row
-            const uint16_t* nv = voxels + (size_t)nb * VXP_CHUNK_VOXELS + (face ? 0 : 31) + 32 * lane;
+            const uint16_t* nv = voxels + (size_t)nb * VXP_CHUNK_VOXELS + (f ? 0 : 31) + 32 * lane;
 #pragma unroll 8
             for (int z = 0; z < 32; ++z) {
                 const uint32_t v = __ldg(nv + 1024 * z);
@@ -259,21 +253,20 @@ __device__ __forceinline__ bool halo_finish(SM& sm, const uint16_t* __restrict__
             }
         }
     }
-    sm.xh[face][lane] = word;
+    sm.xh[f][lane] = word;
     return word != kFull;
 }
 // ------------------------------------------------------------------ active rows
-// actz[z] bit y = row (y,z) has a solid voxel with an air neighbour (halo included).  x_as_air: the x halo is not
-// known yet and counts as air (a superset of the active rows: harmless, they only gate work).
+// actz[z] bit y = row (y,z) has a solid voxel with an air neighbour (halo included).
 template <class SM>
-__device__ __forceinline__ void build_active(SM& sm, bool x_as_air) {
+__device__ __forceinline__ void build_active(SM& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int z = warp * 4 + k, y = lane;
         const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
         const uint32_t c = o[0];
-        const uint32_t lo = x_as_air ? 0u : (sm.xh[0][z] >> y) & 1u, hi = x_as_air ? 0u : (sm.xh[1][z] >> y) & 1u;
+        const uint32_t lo = (sm.xh[0][z] >> y) & 1u, hi = (sm.xh[1][z] >> y) & 1u;
         const uint32_t buried = o[-1] & o[1] & o[-34] & o[34] & ((c << 1) | lo) & ((c >> 1) | (hi << 31));
         const uint32_t act = __ballot_sync(kFull, (c & ~buried) != 0);
         if (lane == 0) sm.actz[z] = act;
@@ -335,13 +328,11 @@ __device__ __forceinline__ void store_quad(unsigned long long* dst, uint32_t rec
 }
 
 // Writes quads [ord0, ord0+cnt) (chunk-local ordinals) of the chunk whose range starts at sm.first.
-// rec_at(i) is the staged record of quad i, finish(rec) completes it (greedy: the run's height, a walk through the
-// sweep log; culled: nothing).  The block ids (origin voxel of the record: independent of the height) are requested
-// BEFORE the records are completed, and both before `before_first()` + the optional barrier, so the latency of the id
-// gather (an L2 round trip) overlaps the height walks and that of the range reservation (a contended global atomic).
-// Returns false if the chunk does not fit the arena.
-template <class SM, class RecFn, class FinFn, class IdFn, class Pre>
-__device__ __forceinline__ bool flush_staging(SM& sm, RecFn rec_at, FinFn finish, uint32_t cnt, uint32_t ord0, const MeshOut& out,
+// The first batch of records and block ids is fetched before `before_first()` + the optional
+// barrier, so the latency of the range reservation (a contended global atomic) overlaps the
+// id gather instead of preceding it.  Returns false if the chunk does not fit the arena.
+template <class SM, class RecFn, class IdFn, class Pre>
+__device__ __forceinline__ bool flush_staging(SM& sm, RecFn rec_at, uint32_t cnt, uint32_t ord0, const MeshOut& out,
                                               IdFn id_of, Pre before_first, bool barrier) {
     const int tid = threadIdx.x;
     uint32_t rec[4], b[4];
@@ -351,9 +342,6 @@ __device__ __forceinline__ bool flush_staging(SM& sm, RecFn rec_at, FinFn finish
         rec[k] = i < cnt ? rec_at(i) : 0u;
         b[k] = i < cnt ? id_of(rec_origin_voxel(rec[k])) : 0u;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (tid + k * kThreads < cnt) rec[k] = finish(rec[k]);
     before_first();
     if (barrier) __syncthreads();
     const unsigned long long first = sm.first;
@@ -368,9 +356,6 @@ __device__ __forceinline__ bool flush_staging(SM& sm, RecFn rec_at, FinFn finish
                 rec[k] = i < cnt ? rec_at(i) : 0u;
                 b[k] = i < cnt ? id_of(rec_origin_voxel(rec[k])) : 0u;
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (i0 + k * kThreads < cnt) rec[k] = finish(rec[k]);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -464,12 +449,6 @@ struct Chain {
     // evenly over the launch instead of sending them through the GPU one after the other.  runs == 0: identity.
     uint32_t runs, run_stride;
 };
-// Chunk of CTA b of a whole-batch launch (see Chain); one 64-bit modulo: call it from one thread.
-__device__ __forceinline__ uint32_t dealt_chunk(const Chain& chain, uint32_t chunk0, uint32_t b) {
-    if (chain.runs != 0u && (b >> 4) < chain.runs)
-        return (uint32_t)(((unsigned long long)(b >> 4) * chain.run_stride) % chain.runs) * 16u + (b & 15u);
-    return chunk0 + b;
-}
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
