@@ -53,10 +53,13 @@ typedef struct vxp_chunk_meta { uint32_t first_quad, quad_count; } vxp_chunk_met
 typedef struct vxp_edit { uint32_t chunk; uint16_t x, y, z, id; } vxp_edit;
 
 /* Batch mesh in DEVICE memory (SPEC §5).  All four arrays are caller-owned.
- * verts must be 32-byte aligned (one quad = one 32-byte store), indices 8-byte aligned. */
+ * verts must be 32-byte aligned (one quad = one 32-byte store), indices 8-byte aligned.
+ * indices may be NULL: the index buffer is then not written at all (SPEC §5 makes it a pure function of the
+ * quad ordinal, 4q + {0,1,2,2,3,0}; a renderer can bind one static index buffer for every mesh) - 24 of the
+ * 56 bytes per quad less to write. */
 typedef struct vxp_mesh_dev {
     uint64_t *verts;          /* 4 * capacity_quads vertices, 8 B each        */
-    uint32_t *indices;        /* 6 * capacity_quads indices                    */
+    uint32_t *indices;        /* 6 * capacity_quads indices, or NULL           */
     vxp_chunk_meta *meta;     /* n entries                                     */
     uint64_t *total_quads;    /* one counter; written by the call (need not be zeroed) */
     uint64_t capacity_quads;
@@ -66,7 +69,7 @@ typedef struct vxp_mesh_dev {
  * next host-level call on the same context or vxp_ctx_destroy. */
 typedef struct vxp_mesh_host {
     const uint64_t *verts;
-    const uint32_t *indices;
+    const uint32_t *indices;  /* NULL after vxp_ctx_set_host_indices(ctx, 0) */
     const vxp_chunk_meta *meta;
     uint64_t total_quads;
 } vxp_mesh_host;
@@ -90,6 +93,9 @@ vxp_status vxp_ctx_reset_stream(vxp_ctx *ctx);
  *     starts early, so freshly produced inputs are safe behind one of those).
  * Results are identical either way. */
 vxp_status vxp_ctx_set_overlap(vxp_ctx *ctx, int enabled);
+/* Host-level calls: whether the index buffer is produced and downloaded (default 1).  With 0, vxp_mesh_host.indices
+ * is NULL, the kernels skip the index writes and 24 of the 56 bytes per quad do not cross PCIe. */
+vxp_status vxp_ctx_set_host_indices(vxp_ctx *ctx, int enabled);
 vxp_status vxp_ctx_synchronize(vxp_ctx *ctx);
 const char *vxp_status_str(vxp_status s);
 /* Detail of the last VXP_ERR_CUDA on this context ("" if none). */
@@ -151,10 +157,11 @@ vxp_status vxp_remesh_edits(vxp_ctx *ctx, uint16_t *d_voxels, const int32_t *d_n
  * capacity_bytes, the records that did not fit have offset UINT64_MAX.  d_packed must be 16-byte aligned. */
 vxp_status vxp_pack_chunks(vxp_ctx *ctx, const uint16_t *d_voxels, uint32_t n, uint8_t *d_packed,
                            uint64_t capacity_bytes, uint64_t *d_offsets, uint64_t *d_total_bytes);
-/* Expand n records into d_voxels (n * 32768 u16).  Malformed records come out as air and make the NEXT
- * vxp_ctx_synchronize return VXP_ERR_BAD_ARG. */
-vxp_status vxp_unpack_chunks(vxp_ctx *ctx, const uint8_t *d_packed, const uint64_t *d_offsets, uint32_t n,
-                             uint16_t *d_voxels);
+/* Expand n records of the packed buffer (packed_bytes long) into d_voxels (n * 32768 u16).  Malformed records - bad
+ * header, or an offset or data that does not lie inside the buffer, such as the UINT64_MAX vxp_pack_chunks gives a
+ * record that did not fit - come out as air and make the NEXT vxp_ctx_synchronize return VXP_ERR_BAD_ARG. */
+vxp_status vxp_unpack_chunks(vxp_ctx *ctx, const uint8_t *d_packed, uint64_t packed_bytes, const uint64_t *d_offsets,
+                             uint32_t n, uint16_t *d_voxels);
 
 /* ---- level of detail (SPEC §11) ------------------------ */
 /* d_out[i] = the 2 x 2 x 2 stored chunks d_child8[i][dx + 2*dy + 4*dz] (indices into d_voxels, -1 = air) at half

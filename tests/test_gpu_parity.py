@@ -626,6 +626,29 @@ def test_unpack_accepts_any_palette_order_and_rejects_malformed(mesher):
     mesher.synchronize()                                       # the verdict is reported once
     with pytest.raises(MeshError):
         mesher.mesh_packed_host(bad, np.zeros(1, np.uint64), None, 1)
+    # offsets that do not lie inside the buffer - the UINT64_MAX that vxp_pack_chunks gives a record that did not fit,
+    # one past the end, a misaligned one, a record whose data runs past the end - are malformed records, not wild reads
+    two = dev(np.concatenate([buf, buf]))
+    for off in (0xFFFFFFFFFFFFFFFF, 2 * len(buf), 8, len(buf) + 16):
+        offs = np.array([0, off], dtype=np.uint64)
+        got = mesher.unpack(two[: len(buf) + 32] if off == len(buf) + 16 else two, dev(offs.view(np.int64)))
+        with pytest.raises(MeshError):
+            mesher.synchronize()
+        g = got.cpu().numpy().view(np.uint16)
+        assert np.array_equal(g[0], vox) and not g[1].any(), hex(off)
+    # ... and packing straight into unpacking after a capacity overflow is such a case
+    vv = np.stack([vox, vox, vox])
+    pk, po, pt = mesher.pack(dev(vv.view(np.int16)), capacity_bytes=2 * len(buf))
+    mesher.synchronize()
+    assert int(pt.item()) == 3 * len(buf)
+    back = mesher.unpack(pk, po)
+    with pytest.raises(MeshError):
+        mesher.synchronize()
+    lost = po.cpu().numpy().view(np.uint64) == np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert lost.sum() == 1
+    b = back.cpu().numpy().view(np.uint16)
+    for i in range(3):
+        assert (not b[i].any()) if lost[i] else np.array_equal(b[i], vox)
 
 
 @pytest.mark.parametrize("mode,mname", MODES)
@@ -851,6 +874,33 @@ def test_terrain_fill_large_batches_bit_exact(mesher):
     assert np.array_equal(host.meta[:, 1], wc) and np.array_equal(_chunk_hashes(host), wh)
 
 
+@pytest.mark.parametrize("mode,mname", MODES)
+def test_meshes_without_an_index_buffer(G, mesher, mode, mname):
+    """vxp_mesh_dev.indices == NULL / vxp_ctx_set_host_indices(0): same vertices, nothing written past them."""
+    import torch
+    vox, nbr = G["terrain42/vox"], G["terrain42/nbr"]
+    want_h, want_c = O.mesh_batch_hash(vox, nbr, mode)
+    out = mesher.alloc_mesh(vox.shape[0], int(want_c.sum()), indices=False)
+    mesher.mesh(dev(vox.view(np.int16)), dev(nbr), mode, out=out)
+    torch.cuda.synchronize()
+    host = out.to_host()
+    assert host.indices.size == 0 and np.array_equal(host.meta[:, 1], want_c) and np.array_equal(_chunk_hashes(host), want_h)
+    mesher.set_host_indices(False)
+    try:
+        for h in (mesher.mesh_host(vox, nbr, mode), mesher.mesh_packed_host(*_packed(vox), nbr, mode)):
+            assert h.indices.size == 0 and np.array_equal(h.meta[:, 1], want_c) and np.array_equal(_chunk_hashes(h), want_h)
+    finally:
+        mesher.set_host_indices(True)
+    h = mesher.mesh_host(vox, nbr, mode)
+    assert h.indices.size == 6 * h.total_quads
+
+
+def _packed(vox):
+    recs = [S.pack_chunk(v) for v in vox]
+    offsets = np.cumsum([0] + [len(r) for r in recs[:-1]]).astype(np.uint64)
+    return np.frombuffer(b"".join(recs), dtype=np.uint8).copy(), offsets
+
+
 def test_default_stream_configuration(G):
     """A Mesher used as constructed (no use_current_torch_stream call): device tensors made on torch's stream, the
     kernels on the stream the Mesher chose, results read back through torch - ordering is the Mesher's job."""
@@ -911,8 +961,8 @@ def test_new_entry_points_reject_bad_arguments_and_accept_empty_batches(mesher):
     assert lib.vxp_pack_chunks(h, None, 2, buf.data_ptr(), 1 << 18, off.data_ptr(), tot.data_ptr()) == BAD
     assert lib.vxp_pack_chunks(h, vox.data_ptr(), 2, buf.data_ptr() + 8, 1 << 17, off.data_ptr(), tot.data_ptr()) == BAD
     assert lib.vxp_pack_chunks(h, vox.data_ptr(), 0, None, 0, None, tot.data_ptr()) == OK
-    assert lib.vxp_unpack_chunks(h, None, off.data_ptr(), 2, vox.data_ptr()) == BAD
-    assert lib.vxp_unpack_chunks(h, buf.data_ptr(), off.data_ptr(), 0, None) == OK
+    assert lib.vxp_unpack_chunks(h, None, 0, off.data_ptr(), 2, vox.data_ptr()) == BAD
+    assert lib.vxp_unpack_chunks(h, buf.data_ptr(), buf.numel(), off.data_ptr(), 0, None) == OK
     kids = torch.full((1, 8), -1, dtype=torch.int32, device="cuda")
     assert lib.vxp_downsample_chunks(h, vox.data_ptr(), None, 1, vox.data_ptr()) == BAD
     assert lib.vxp_downsample_chunks(h, vox.data_ptr(), kids.data_ptr(), 0, None) == OK

@@ -2,6 +2,7 @@
 
   python tools/ncu_summary.py launches <launches.csv> <out.csv>       # per-launch durations + per-kernel share
   python tools/ncu_summary.py kernel <raw.csv> <source.csv> <out.txt>  # key counters + hottest source lines
+  python tools/ncu_summary.py traffic <out.json> <label>=<raw.csv>[@<report name>] ...   # DRAM bytes per launch, read by bench.py
 (raw.csv: `ncu -i X.ncu-rep --page raw --csv`; source.csv: `--page source --print-source cuda,sass --csv`)
 """
 import csv, subprocess, sys, collections
@@ -59,5 +60,34 @@ def kernel(raw, source, dst):
                                capture_output=True, text=True).stdout)
 
 
+def traffic(dst, *pairs):
+    """profiles/ncu_traffic.json: dram__bytes_read.sum / dram__bytes_write.sum per launch (mean over the captured launches)
+    of each labelled kernel, with the commit the capture was taken at.  bench.py reads `roofline.traffic` from it."""
+    import json, os
+    def to_bytes(v, unit):
+        f = float(v.replace(",", ""))
+        return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    try:
+        old = json.load(open(dst))
+    except Exception:
+        old = {"kernels": {}}
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    for pair in pairs:
+        label, rest = pair.split("=", 1)
+        path, _, report = rest.partition("@")
+        rows = list(csv.reader(open(path)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        rd = [to_bytes(r[ir], units[ir]) for r in data]
+        wr = [to_bytes(r[iw], units[iw]) for r in data]
+        old["kernels"][label] = {"dram_read_bytes": sum(rd) / len(rd), "dram_write_bytes": sum(wr) / len(wr), "launches": len(data),
+                                 "duration_us_under_ncu": sum(float(r[it].replace(",", "")) for r in data) / len(data) / (1e3 if units[it] in ("ns", "nsecond") else 1.0),
+                                 "ncu_kernel_name": data[0][hdr.index("Kernel Name")] if "Kernel Name" in hdr else None,
+                                 "report": report or os.path.basename(path), "commit": commit}
+    old["commit"] = commit
+    old["how"] = "ncu --set full --clock-control none, one launch at a time (cold L2, serialised); bytes are per launch"
+    json.dump(old, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "kernel": kernel, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

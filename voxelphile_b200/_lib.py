@@ -43,6 +43,7 @@ SIGNATURES = {
     "vxp_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxp_ctx_reset_stream": (C.c_int, [C.c_void_p]),
     "vxp_ctx_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
+    "vxp_ctx_set_host_indices": (C.c_int, [C.c_void_p, C.c_int]),
     "vxp_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "vxp_status_str": (C.c_char_p, [C.c_int]),
     "vxp_last_error": (C.c_char_p, [C.c_void_p]),
@@ -62,7 +63,7 @@ SIGNATURES = {
     "vxp_remesh_edits_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(MeshHost),
                               C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "vxp_pack_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
-    "vxp_unpack_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "vxp_unpack_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p]),
     "vxp_mesh_packed_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                              C.c_int, C.POINTER(MeshHost)]),
     "vxp_downsample_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),

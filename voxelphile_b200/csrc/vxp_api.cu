@@ -33,6 +33,7 @@ struct vxp_ctx {
     unsigned long long* d_counters = nullptr;   // one zero-initialised launch counter per slot
     int slot = 0;
     int overlap = 0;                            // vxp_ctx_set_overlap
+    int host_indices = 1;                       // vxp_ctx_set_host_indices
     bool launched = false;                      // a mesh launch has been enqueued ...
     cudaStream_t launch_stream = nullptr;       // ... on this stream
     bool chain_open = false;                    // ... with overlap enabled, and nothing else of ours since
@@ -244,7 +245,7 @@ bool valid_mode(vxp_mode m) { return m == VXP_MODE_CULLED || m == VXP_MODE_GREED
 bool valid_out(const vxp_mesh_dev* o, uint32_t n) {
     if (!o || !o->total_quads) return false;
     if (n && !o->meta) return false;
-    if (o->capacity_quads && (!o->verts || !o->indices)) return false;
+    if (o->capacity_quads && !o->verts) return false;    // indices may be NULL: not written
     if ((reinterpret_cast<uintptr_t>(o->verts) & 31u) || (reinterpret_cast<uintptr_t>(o->indices) & 7u)) return false;
     if (o->capacity_quads > 0xFFFFFFFEull) return false;  // first_quad is a u32; 0xFFFFFFFF is the overflow mark
     return true;
@@ -259,7 +260,7 @@ vxp_status mesh_into_host(vxp_ctx* ctx, uint32_t n, Launch launch, vxp_mesh_host
     if ((s = grow_quads(ctx, (size_t)n * 64 + 4096)) != VXP_OK) return s;  // first guess; grows below
     uint64_t total = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
-        vxp_mesh_dev dev{ctx->d_verts, ctx->d_indices, ctx->d_meta, ctx->d_total, ctx->quads_cap};
+        vxp_mesh_dev dev{ctx->d_verts, ctx->host_indices ? ctx->d_indices : nullptr, ctx->d_meta, ctx->d_total, ctx->quads_cap};
         VXP_CUDA(ctx, launch(dev));   // counts itself in ctx->launches
         VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_total, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                       ctx->stream));
@@ -276,13 +277,14 @@ vxp_status mesh_into_host(vxp_ctx* ctx, uint32_t n, Launch launch, vxp_mesh_host
     if (total) {
         VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_verts, ctx->d_verts, total * 4 * sizeof(uint64_t),
                                       cudaMemcpyDeviceToHost, ctx->stream));
-        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices, ctx->d_indices, total * 6 * sizeof(uint32_t),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->host_indices)
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices, ctx->d_indices, total * 6 * sizeof(uint32_t),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
     }
     VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->chain_open = false;
     out->verts = ctx->h_verts;
-    out->indices = ctx->h_indices;
+    out->indices = ctx->host_indices ? ctx->h_indices : nullptr;
     out->meta = ctx->h_meta;
     out->total_quads = total;
     return VXP_OK;
@@ -412,6 +414,12 @@ vxp_status vxp_ctx_set_overlap(vxp_ctx* ctx, int enabled) {
     if (!ctx) return VXP_ERR_BAD_ARG;
     ctx->overlap = enabled ? 1 : 0;
     ctx->chain_open = false;
+    return VXP_OK;
+}
+
+vxp_status vxp_ctx_set_host_indices(vxp_ctx* ctx, int enabled) {
+    if (!ctx) return VXP_ERR_BAD_ARG;
+    ctx->host_indices = enabled ? 1 : 0;
     return VXP_OK;
 }
 
@@ -617,7 +625,8 @@ vxp_status vxp_pack_chunks(vxp_ctx* ctx, const uint16_t* d_voxels, uint32_t n, u
     return VXP_OK;
 }
 
-vxp_status vxp_unpack_chunks(vxp_ctx* ctx, const uint8_t* d_packed, const uint64_t* d_offsets, uint32_t n, uint16_t* d_voxels) {
+vxp_status vxp_unpack_chunks(vxp_ctx* ctx, const uint8_t* d_packed, uint64_t packed_bytes, const uint64_t* d_offsets, uint32_t n,
+                             uint16_t* d_voxels) {
     if (!ctx || (n && (!d_packed || !aligned16(d_packed) || !d_offsets || !d_voxels || !aligned16(d_voxels)))) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     ctx->chain_open = false;
@@ -626,7 +635,7 @@ vxp_status vxp_unpack_chunks(vxp_ctx* ctx, const uint8_t* d_packed, const uint64
         VXP_CUDA(ctx, cudaMemcpy(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (*ctx->h_status) { ctx->status_pending = false; return VXP_ERR_BAD_ARG; }
     }
-    VXP_CUDA(ctx, vxp::launch_unpack_chunks(d_packed, reinterpret_cast<const unsigned long long*>(d_offsets), n, d_voxels,
+    VXP_CUDA(ctx, vxp::launch_unpack_chunks(d_packed, packed_bytes, reinterpret_cast<const unsigned long long*>(d_offsets), n, d_voxels,
                                             ctx->d_status, ctx->stream));
     ctx->launches += n ? 1 : 0;
     ctx->status_pending = n != 0;
@@ -714,7 +723,7 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
         ctx->launched = true;
         ctx->launch_stream = ctx->stream;
         ctx->chain_open = false;
-        const vxp_mesh_dev dev{ctx->d_verts, ctx->d_indices, ctx->d_meta, ctx->d_total, ctx->quads_cap};
+        const vxp_mesh_dev dev{ctx->d_verts, ctx->host_indices ? ctx->d_indices : nullptr, ctx->d_meta, ctx->d_total, ctx->quads_cap};
         // uploads: neighbour table and read-only halo chunks first, then the slices in order
         VXP_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
         VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
@@ -750,8 +759,9 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
             if (!overflow && t > prev) {
                 VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_verts + prev * 4, ctx->d_verts + prev * 4, (t - prev) * 4 * sizeof(uint64_t),
                                               cudaMemcpyDeviceToHost, ctx->s_out));
-                VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices + prev * 6, ctx->d_indices + prev * 6, (t - prev) * 6 * sizeof(uint32_t),
-                                              cudaMemcpyDeviceToHost, ctx->s_out));
+                if (ctx->host_indices)
+                    VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices + prev * 6, ctx->d_indices + prev * 6, (t - prev) * 6 * sizeof(uint32_t),
+                                                  cudaMemcpyDeviceToHost, ctx->s_out));
             }
             prev = t;
         }
@@ -774,7 +784,7 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
     };
     if (done || n == 0) {
         out->verts = ctx->h_verts;
-        out->indices = ctx->h_indices;
+        out->indices = ctx->host_indices ? ctx->h_indices : nullptr;
         out->meta = ctx->h_meta;
         out->total_quads = total;
         resident();
@@ -845,7 +855,7 @@ vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t pa
         VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_packed, packed, packed_bytes, cudaMemcpyHostToDevice, ctx->stream));
         VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, offsets, (size_t)n_stored * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         if (nbr6) VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        VXP_CUDA(ctx, vxp::launch_unpack_chunks(ctx->d_packed, ctx->d_offsets, n_stored, ctx->d_voxels, ctx->d_status, ctx->stream));
+        VXP_CUDA(ctx, vxp::launch_unpack_chunks(ctx->d_packed, packed_bytes, ctx->d_offsets, n_stored, ctx->d_voxels, ctx->d_status, ctx->stream));
         ctx->launches += 1;
     }
     const int greedy = mode == VXP_MODE_GREEDY;
@@ -886,7 +896,7 @@ vxp_status vxp_remesh_edits_host(vxp_ctx* ctx, const vxp_edit* edits, uint32_t m
     uint32_t cnt = 0;
     if (m) VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_edits, edits, (size_t)m * sizeof(vxp_edit), cudaMemcpyHostToDevice, ctx->stream));
     for (int attempt = 0; attempt < 2; ++attempt) {
-        const vxp_mesh_dev dev{ctx->d_verts, ctx->d_indices, ctx->d_meta, ctx->d_total, ctx->quads_cap};
+        const vxp_mesh_dev dev{ctx->d_verts, ctx->host_indices ? ctx->d_indices : nullptr, ctx->d_meta, ctx->d_total, ctx->quads_cap};
         if (attempt == 0) {
             s = vxp_remesh_edits(ctx, ctx->d_voxels, ctx->world_has_nbr ? ctx->d_nbr6 : nullptr, n, ctx->d_edits, m, mode,
                                  ctx->d_dirty, ctx->d_dirty_count, &dev);
@@ -915,11 +925,12 @@ vxp_status vxp_remesh_edits_host(vxp_ctx* ctx, const vxp_edit* edits, uint32_t m
     if ((s = grow_host_quads(ctx, total)) != VXP_OK) return s;
     if (total) {
         VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_verts, ctx->d_verts, total * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices, ctx->d_indices, total * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->host_indices)
+            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_indices, ctx->d_indices, total * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     out->verts = ctx->h_verts;
-    out->indices = ctx->h_indices;
+    out->indices = ctx->host_indices ? ctx->h_indices : nullptr;
     out->meta = ctx->h_meta;
     out->total_quads = total;
     *dirty = ctx->h_dirty;

@@ -72,8 +72,8 @@ cudaError_t launch_mesh_list(const uint16_t* d_voxels, const int32_t* d_nbr6, ui
 // the batch needs (records that do not fit get offset ~0).  d_status: one word, zeroed here, 1 = malformed record.
 cudaError_t launch_pack_chunks(const uint16_t* d_voxels, uint32_t n, unsigned char* d_packed, unsigned long long capacity,
                                unsigned long long* d_offsets, unsigned long long* d_total, cudaStream_t stream);
-cudaError_t launch_unpack_chunks(const unsigned char* d_packed, const unsigned long long* d_offsets, uint32_t n,
-                                 uint16_t* d_voxels, uint32_t* d_status, cudaStream_t stream);
+cudaError_t launch_unpack_chunks(const unsigned char* d_packed, unsigned long long packed_bytes, const unsigned long long* d_offsets,
+                                 uint32_t n, uint16_t* d_voxels, uint32_t* d_status, cudaStream_t stream);
 // LOD (SPEC §11): out[i] = half-resolution chunk of the 2x2x2 stored chunks child8[i][dx + 2 dy + 4 dz] (-1 = air).
 cudaError_t launch_downsample_chunks(const uint16_t* d_voxels, const int32_t* d_child8, uint32_t n_out, uint16_t* d_out,
                                      cudaStream_t stream);

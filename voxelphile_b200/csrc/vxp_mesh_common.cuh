@@ -364,6 +364,7 @@ __device__ __forceinline__ bool flush_staging(SM& sm, RecFn rec_at, uint32_t cnt
         }
     }
     // indices: 8-byte pairs, three per quad -> a warp stores 256 contiguous bytes
+    if (out.indices == nullptr) return true;           // the caller binds a static index buffer (vxp_mesh_dev.indices == NULL)
     uint32_t* const idst = out.indices + (first + ord0) * 6;
     uint32_t j = (uint32_t)tid / 3u, part = (uint32_t)tid - 3u * j;
     for (uint32_t i = tid; i < 3 * cnt; i += kThreads) {

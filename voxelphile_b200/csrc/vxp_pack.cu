@@ -127,8 +127,9 @@ __global__ void __launch_bounds__(kThreads) pack_chunks_kernel(const uint16_t* _
     }
 }
 
-// status[0] is set to 1 if any record is malformed (bad magic / bits / palette length); such chunks come out as air.
-__global__ void __launch_bounds__(kThreads) unpack_chunks_kernel(const unsigned char* __restrict__ packed,
+// status[0] is set to 1 if any record is malformed (offset outside the buffer - vxp_pack_chunks marks records that did
+// not fit with ~0 -, misaligned, bad magic / bits / palette length, data running past the end); such chunks come out as air.
+__global__ void __launch_bounds__(kThreads) unpack_chunks_kernel(const unsigned char* __restrict__ packed, unsigned long long packed_bytes,
                                                                   const unsigned long long* __restrict__ offsets, uint32_t n,
                                                                   uint16_t* __restrict__ voxels, uint32_t* __restrict__ status) {
     __shared__ uint32_t s_pal[16];
@@ -136,16 +137,24 @@ __global__ void __launch_bounds__(kThreads) unpack_chunks_kernel(const unsigned 
     const int tid = threadIdx.x;
     const uint32_t chunk = blockIdx.x;
     if (chunk >= n) return;
-    const unsigned char* rec = packed + offsets[chunk];
+    const unsigned long long off = offsets[chunk];
+    const bool in_buffer = (off & 15ull) == 0ull && off <= packed_bytes && packed_bytes - off >= (unsigned long long)kHeaderBytes;   // block-uniform
+    const unsigned char* rec = packed + (in_buffer ? off : 0ull);
     if (tid == 0) {
-        const uint32_t* h = reinterpret_cast<const uint32_t*>(rec);
-        const uint32_t bits = h[1] & 0xFFFFu, len = h[1] >> 16;
-        const bool ok = h[0] == kMagic && (bits == 0u || bits == 1u || bits == 2u || bits == 4u || bits == 16u) &&
-                        h[2] == 4096u * bits && (bits == 16u ? len == 0u : (len >= 1u && len <= 16u && len <= (1u << bits)));
+        bool ok = in_buffer;
+        uint32_t bits = 0;
+        if (ok) {
+            const uint32_t* h = reinterpret_cast<const uint32_t*>(rec);
+            bits = h[1] & 0xFFFFu;
+            const uint32_t len = h[1] >> 16;
+            ok = h[0] == kMagic && (bits == 0u || bits == 1u || bits == 2u || bits == 4u || bits == 16u) &&
+                 h[2] == 4096u * bits && (bits == 16u ? len == 0u : (len >= 1u && len <= 16u && len <= (1u << bits))) &&
+                 packed_bytes - off - (unsigned long long)kHeaderBytes >= (unsigned long long)h[2];
+        }
         if (!ok) atomicExch(status, 1u);
         s_bits = ok ? bits : 0xFFu;
     }
-    if (tid < 8) {
+    if (tid < 8 && in_buffer) {
         const uint32_t p = reinterpret_cast<const uint32_t*>(rec + 16)[tid];
         s_pal[2 * tid] = p & 0xFFFFu;
         s_pal[2 * tid + 1] = p >> 16;
@@ -193,11 +202,11 @@ cudaError_t launch_pack_chunks(const uint16_t* d_voxels, uint32_t n, unsigned ch
     return cudaGetLastError();
 }
 
-cudaError_t launch_unpack_chunks(const unsigned char* d_packed, const unsigned long long* d_offsets, uint32_t n,
-                                 uint16_t* d_voxels, uint32_t* d_status, cudaStream_t stream) {
+cudaError_t launch_unpack_chunks(const unsigned char* d_packed, unsigned long long packed_bytes, const unsigned long long* d_offsets,
+                                 uint32_t n, uint16_t* d_voxels, uint32_t* d_status, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(d_status, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess || n == 0) return e;
-    unpack_chunks_kernel<<<n, kThreads, 0, stream>>>(d_packed, d_offsets, n, d_voxels, d_status);
+    unpack_chunks_kernel<<<n, kThreads, 0, stream>>>(d_packed, packed_bytes, d_offsets, n, d_voxels, d_status);
     return cudaGetLastError();
 }
 

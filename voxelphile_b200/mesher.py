@@ -66,7 +66,7 @@ class DeviceMesh:
     """Batch mesh in device memory (SPEC §5). ``verts`` holds u64 bit patterns in int64."""
 
     verts: "torch.Tensor"    # int64 [4*capacity]
-    indices: "torch.Tensor"  # int32 [6*capacity]
+    indices: "Optional[torch.Tensor]"  # int32 [6*capacity], or None (not written)
     meta: "torch.Tensor"     # int32 [n,2]  (first_quad, quad_count)
     total: "torch.Tensor"    # int64 [1]
     capacity: int
@@ -77,7 +77,7 @@ class DeviceMesh:
             raise MeshError(_lib.VXP_ERR_CAPACITY, f"need {total} quads, capacity {self.capacity}")
         return HostMesh(
             verts=self.verts[: 4 * total].cpu().numpy().view(np.uint64),
-            indices=self.indices[: 6 * total].cpu().numpy().view(np.uint32),
+            indices=self.indices[: 6 * total].cpu().numpy().view(np.uint32) if self.indices is not None else np.empty(0, np.uint32),
             meta=self.meta.cpu().numpy().view(np.uint32).reshape(-1, 2),
             total_quads=total,
         )
@@ -93,8 +93,8 @@ class HostMesh:
     def chunk(self, i: int):
         """(verts[cnt,4], indices[cnt,6]) of chunk i."""
         first, cnt = int(self.meta[i, 0]), int(self.meta[i, 1])
-        return (self.verts[4 * first : 4 * (first + cnt)].reshape(cnt, 4),
-                self.indices[6 * first : 6 * (first + cnt)].reshape(cnt, 6))
+        ix = self.indices[6 * first : 6 * (first + cnt)].reshape(cnt, 6) if self.indices.size else self.indices.reshape(0, 6)
+        return self.verts[4 * first : 4 * (first + cnt)].reshape(cnt, 4), ix
 
 
 class Mesher:
@@ -144,6 +144,11 @@ class Mesher:
         between two output meshes and does not rewrite a call's inputs behind the previous call."""
         self._check(self._lib.vxp_ctx_set_overlap(self._h, 1 if enabled else 0))
 
+    def set_host_indices(self, enabled: bool):
+        """vxp_ctx_set_host_indices: with False the host-level calls neither produce nor download the index buffer
+        (``HostMesh.indices`` is then empty: SPEC §5 makes it 4q + {0,1,2,2,3,0})."""
+        self._check(self._lib.vxp_ctx_set_host_indices(self._h, 1 if enabled else 0))
+
     def use_stream(self, stream: Optional["torch.cuda.Stream"]):
         """Pin a torch stream; ``None`` selects the context's own non-blocking stream (see the class docstring)."""
         self._follow = False
@@ -176,13 +181,14 @@ class Mesher:
         import torch
         return torch.device("cuda", self.device)
 
-    def alloc_mesh(self, n: int, capacity: int) -> DeviceMesh:
+    def alloc_mesh(self, n: int, capacity: int, indices: bool = True) -> DeviceMesh:
+        """indices=False: no index buffer (vxp_mesh_dev.indices == NULL: the kernels do not write indices)."""
         self._on_torch_stream()
         import torch
         d = self._dev()
         return DeviceMesh(
             verts=torch.empty(4 * max(capacity, 1), dtype=torch.int64, device=d),
-            indices=torch.empty(6 * max(capacity, 1), dtype=torch.int32, device=d),
+            indices=torch.empty(6 * max(capacity, 1), dtype=torch.int32, device=d) if indices else None,
             meta=torch.zeros((n, 2), dtype=torch.int32, device=d),
             total=torch.zeros(1, dtype=torch.int64, device=d),
             capacity=capacity,
@@ -190,8 +196,8 @@ class Mesher:
 
     @staticmethod
     def _mesh_struct(m: DeviceMesh) -> _lib.MeshDev:
-        return _lib.MeshDev(m.verts.data_ptr(), m.indices.data_ptr(), m.meta.data_ptr(), m.total.data_ptr(),
-                            m.capacity)
+        return _lib.MeshDev(m.verts.data_ptr(), m.indices.data_ptr() if m.indices is not None else None, m.meta.data_ptr(),
+                            m.total.data_ptr(), m.capacity)
 
     def terrain_fill(self, coords: "torch.Tensor", seed: int, out: Optional["torch.Tensor"] = None):
         """coords: int32 [n,3] on this device -> int16 [n,32768] (u16 bit patterns)."""
@@ -313,7 +319,8 @@ class Mesher:
         n = int(offsets.shape[0])
         if out is None:
             out = torch.empty((n, CHUNK_VOXELS), dtype=torch.int16, device=packed.device)
-        self._check(self._lib.vxp_unpack_chunks(self._h, packed.data_ptr(), offsets.data_ptr(), n, out.data_ptr()))
+        self._check(self._lib.vxp_unpack_chunks(self._h, packed.data_ptr(), packed.numel() * packed.element_size(), offsets.data_ptr(),
+                                                n, out.data_ptr()))
         return out
 
     def mesh_packed_host(self, packed: np.ndarray, offsets: np.ndarray, nbr6: Optional[np.ndarray], mode: int,
@@ -362,7 +369,7 @@ class Mesher:
             a = np.frombuffer(buf, dtype=dtype, count=count)
             return a.copy() if copy else a
 
-        return HostMesh(view(h.verts, 4 * q, np.uint64), view(h.indices, 6 * q, np.uint32),
+        return HostMesh(view(h.verts, 4 * q, np.uint64), view(h.indices, 6 * q if h.indices else 0, np.uint32),
                         view(h.meta, 2 * n, np.uint32).reshape(n, 2), q)
 
     def mesh_host(self, voxels: np.ndarray, nbr6: Optional[np.ndarray], mode: int, copy: bool = True,
