@@ -3,14 +3,72 @@
 // point ends in a kernel launch or an error.
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/vxp.h"
 #include "vxp_launch.h"
+
+// A few host threads that copy a caller's PAGEABLE buffer into pinned staging memory in parallel (one memcpy thread moves
+// ~10 GB/s, a PCIe 5 x16 link 55): created on the first host-level call that is handed pageable memory.
+struct CopyPool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    size_t bytes = 0;
+    uint64_t generation = 0;
+    unsigned pending = 0;
+    bool stop = false;
+
+    explicit CopyPool(unsigned threads) {
+        for (unsigned t = 0; t < threads; ++t) workers.emplace_back([this, t, threads] { run(t, threads); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            stop = true;
+        }
+        cv_job.notify_all();
+        for (auto& w : workers) w.join();
+    }
+    void run(unsigned t, unsigned threads) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_job.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            const size_t piece = ((bytes + threads - 1) / threads + 4095) & ~(size_t)4095;
+            const size_t lo = (size_t)t * piece, hi = lo + piece < bytes ? lo + piece : bytes;
+            const unsigned char* s_ = src;
+            unsigned char* d_ = dst;
+            lk.unlock();
+            if (lo < hi) std::memcpy(d_ + lo, s_ + lo, hi - lo);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    void copy(void* d, const void* s_, size_t n) {   // returns when the bytes are in place
+        std::unique_lock<std::mutex> lk(mu);
+        src = static_cast<const unsigned char*>(s_);
+        dst = static_cast<unsigned char*>(d);
+        bytes = n;
+        pending = (unsigned)workers.size();
+        ++generation;
+        cv_job.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
 
 struct vxp_ctx {
     int device = 0;
@@ -61,6 +119,12 @@ struct vxp_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
     uint64_t* h_totals = nullptr;   // pinned, kMaxSlices entries
+    // uploads from pageable caller memory: two pinned staging buffers used alternately, filled by the copy pool
+    static constexpr size_t kStageBytes = (size_t)32 << 20;
+    unsigned char* h_stage[2] = {};
+    cudaEvent_t ev_stage[2] = {};
+    int stage_next = 0;
+    CopyPool* pool = nullptr;
 };
 
 namespace {
@@ -89,6 +153,45 @@ struct DeviceGuard {
 };
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Host -> device copy of a caller buffer on `stream`.  Pinned (or otherwise CUDA-registered) memory goes straight to
+// cudaMemcpyAsync.  Pageable memory (a plain malloc / Vec<u16>) would make the driver stage the copy through its own
+// small bounce buffer at ~11 GB/s, a fifth of the link: instead the context's copy pool moves it, 32 MiB at a time, into
+// two pinned staging buffers used alternately, each followed by its own asynchronous copy - the memcpy of piece k+1
+// overlaps the transfer of piece k.  The source may be re-used by the caller when the call returns.
+vxp_status upload(vxp_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream) {
+    if (bytes == 0) return VXP_OK;
+    cudaPointerAttributes attr{};
+    bool pageable = true;
+    if (cudaPointerGetAttributes(&attr, h_src) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+    if (!pageable || bytes < ((size_t)1 << 20)) {
+        VXP_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
+        return VXP_OK;
+    }
+    if (!ctx->pool) {
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned threads = hw >= 16 ? 8u : hw >= 4 ? hw / 2 : 1u;
+        ctx->pool = new (std::nothrow) CopyPool(threads);
+        if (!ctx->pool) return VXP_ERR_OOM;
+        for (int k = 0; k < 2; ++k) {
+            VXP_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stage[k]), vxp_ctx::kStageBytes));
+            VXP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[k], cudaEventDisableTiming));
+        }
+    }
+    const unsigned char* src = static_cast<const unsigned char*>(h_src);
+    unsigned char* dst = static_cast<unsigned char*>(d_dst);
+    for (size_t off = 0; off < bytes; off += vxp_ctx::kStageBytes) {
+        const size_t n = bytes - off < vxp_ctx::kStageBytes ? bytes - off : vxp_ctx::kStageBytes;
+        const int b = ctx->stage_next;
+        ctx->stage_next ^= 1;
+        VXP_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage[b]));       // the transfer that last used this buffer is done
+        ctx->pool->copy(ctx->h_stage[b], src + off, n);
+        VXP_CUDA(ctx, cudaMemcpyAsync(dst + off, ctx->h_stage[b], n, cudaMemcpyHostToDevice, stream));
+        VXP_CUDA(ctx, cudaEventRecord(ctx->ev_stage[b], stream));
+    }
+    return VXP_OK;
+}
 
 template <class T>
 vxp_status grow_device(vxp_ctx* ctx, T** p, size_t* cap, size_t need, size_t elems_per_unit) {
@@ -393,6 +496,11 @@ void vxp_ctx_destroy(vxp_ctx* ctx) {
     for (int k = 0; k < vxp_ctx::kMaxSlices; ++k) {
         if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
         if (ctx->ev_k[k]) cudaEventDestroy(ctx->ev_k[k]);
+    }
+    delete ctx->pool;
+    for (int k = 0; k < 2; ++k) {
+        cudaFreeHost(ctx->h_stage[k]);
+        if (ctx->ev_stage[k]) cudaEventDestroy(ctx->ev_stage[k]);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -730,24 +838,29 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
         VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
         if (nbr6)
             VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_in));
-        if (n_stored > n)
-            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels + (size_t)n * VXP_CHUNK_VOXELS, voxels + (size_t)n * VXP_CHUNK_VOXELS,
-                                          (size_t)(n_stored - n) * chunk_bytes, cudaMemcpyHostToDevice, ctx->s_in));
+        if (n_stored > n &&
+            (s = upload(ctx, ctx->d_voxels + (size_t)n * VXP_CHUNK_VOXELS, voxels + (size_t)n * VXP_CHUNK_VOXELS,
+                        (size_t)(n_stored - n) * chunk_bytes, ctx->s_in)) != VXP_OK)
+            return s;
+        // kernels: slice j as soon as slice need[j] is on the device (enqueued right behind that upload, so that with
+        // pageable caller memory - where this thread spends the call copying into the staging buffers - the first
+        // kernels and downloads do not wait for the last upload); the running total follows each one to the host
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_total, 0, sizeof(uint64_t), ctx->stream));
+        uint32_t launched = 0;
         for (uint32_t k = 0; k < S; ++k) {
             const uint32_t lo = k * slice, hi = lo + slice < n ? lo + slice : n;
-            if (lo < hi)
-                VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels + (size_t)lo * VXP_CHUNK_VOXELS, voxels + (size_t)lo * VXP_CHUNK_VOXELS,
-                                              (size_t)(hi - lo) * chunk_bytes, cudaMemcpyHostToDevice, ctx->s_in));
+            if (lo < hi && (s = upload(ctx, ctx->d_voxels + (size_t)lo * VXP_CHUNK_VOXELS, voxels + (size_t)lo * VXP_CHUNK_VOXELS,
+                                       (size_t)(hi - lo) * chunk_bytes, ctx->s_in)) != VXP_OK)
+                return s;
             VXP_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[k], ctx->s_in));
-        }
-        // kernels: slice k once slice need[k] is on the device; the running total follows each one to the host
-        VXP_CUDA(ctx, cudaMemsetAsync(ctx->d_total, 0, sizeof(uint64_t), ctx->stream));
-        for (uint32_t k = 0; k < S; ++k) {
-            VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[need[k]], 0));
-            VXP_CUDA(ctx, vxp::launch_mesh_range(ctx->d_voxels, d_nbr, n, k * slice, (k + 1) * slice, greedy, dev, scratch, ctx->stream));
-            ctx->launches += 1;
-            VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_totals + k, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-            VXP_CUDA(ctx, cudaEventRecord(ctx->ev_k[k], ctx->stream));
+            while (launched < S && need[launched] <= k) {
+                const uint32_t j = launched++;
+                VXP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[need[j]], 0));
+                VXP_CUDA(ctx, vxp::launch_mesh_range(ctx->d_voxels, d_nbr, n, j * slice, (j + 1) * slice, greedy, dev, scratch, ctx->stream));
+                ctx->launches += 1;
+                VXP_CUDA(ctx, cudaMemcpyAsync(ctx->h_totals + j, ctx->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+                VXP_CUDA(ctx, cudaEventRecord(ctx->ev_k[j], ctx->stream));
+            }
         }
         // downloads: the quads of slice k as soon as its kernel is done
         uint64_t prev = 0;
@@ -852,7 +965,7 @@ vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t pa
     if (ctx->status_pending && (s = vxp_ctx_synchronize(ctx)) != VXP_OK) return s;   // an earlier vxp_unpack_chunks verdict is not lost
     const int32_t* d_nbr = nbr6 ? ctx->d_nbr6 : nullptr;
     if (n_stored) {
-        VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_packed, packed, packed_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if ((s = upload(ctx, ctx->d_packed, packed, packed_bytes, ctx->stream)) != VXP_OK) return s;
         VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, offsets, (size_t)n_stored * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         if (nbr6) VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         VXP_CUDA(ctx, vxp::launch_unpack_chunks(ctx->d_packed, packed_bytes, ctx->d_offsets, n_stored, ctx->d_voxels, ctx->d_status, ctx->stream));
