@@ -74,6 +74,7 @@ extern "C" {
     pub fn vxp_ctx_set_stream(ctx: *mut vxp_ctx, cuda_stream: *mut c_void) -> vxp_status;
     pub fn vxp_ctx_reset_stream(ctx: *mut vxp_ctx) -> vxp_status;
     pub fn vxp_ctx_set_overlap(ctx: *mut vxp_ctx, enabled: c_int) -> vxp_status;
+    pub fn vxp_ctx_set_host_indices(ctx: *mut vxp_ctx, enabled: c_int) -> vxp_status;
     pub fn vxp_ctx_synchronize(ctx: *mut vxp_ctx) -> vxp_status;
     pub fn vxp_status_str(s: vxp_status) -> *const c_char;
     pub fn vxp_last_error(ctx: *const vxp_ctx) -> *const c_char;
@@ -101,7 +102,7 @@ extern "C" {
 
     pub fn vxp_pack_chunks(ctx: *mut vxp_ctx, d_voxels: *const u16, n: u32, d_packed: *mut u8, capacity_bytes: u64,
                            d_offsets: *mut u64, d_total_bytes: *mut u64) -> vxp_status;
-    pub fn vxp_unpack_chunks(ctx: *mut vxp_ctx, d_packed: *const u8, d_offsets: *const u64, n: u32,
+    pub fn vxp_unpack_chunks(ctx: *mut vxp_ctx, d_packed: *const u8, packed_bytes: u64, d_offsets: *const u64, n: u32,
                              d_voxels: *mut u16) -> vxp_status;
 
     pub fn vxp_downsample_chunks(ctx: *mut vxp_ctx, d_voxels: *const u16, d_child8: *const i32, n_out: u32,

@@ -43,7 +43,8 @@ pub struct Chunk {
     pub voxels: Box<[BlockId; CHUNK_VOXELS]>,
 }
 
-/// Packed vertices (8 B) and indices of one chunk (SPEC.md §5).
+/// Packed vertices (8 B) and indices of one chunk (SPEC.md §5).  `indices` is empty after
+/// [`Mesher::set_indices`]`(false)`: SPEC §5 makes them `4q + {0,1,2,2,3,0}`, one static buffer serves every mesh.
 pub struct Mesh {
     pub vertices: Vec<u64>,
     pub indices: Vec<u32>,
@@ -61,6 +62,11 @@ impl Mesher {
         let mut ctx = ptr::null_mut();
         check(unsafe { sys::vxp_ctx_create(device, &mut ctx) })?;
         Ok(Mesher { ctx })
+    }
+
+    /// Whether host results carry an index buffer (default true; `vxp_ctx_set_host_indices`).
+    pub fn set_indices(&mut self, enabled: bool) -> Result<(), MeshError> {
+        check(unsafe { sys::vxp_ctx_set_host_indices(self.ctx, enabled as i32) })
     }
 
     /// Neighbour table of a coordinate list (-1 = no chunk on that side).
@@ -159,7 +165,8 @@ unsafe fn split(host: &sys::vxp_mesh_host, n: usize) -> Vec<Mesh> {
             }
             Mesh {
                 vertices: std::slice::from_raw_parts(host.verts.add(4 * first), 4 * cnt).to_vec(),
-                indices: std::slice::from_raw_parts(host.indices.add(6 * first), 6 * cnt).to_vec(),
+                indices: if host.indices.is_null() { Vec::new() }
+                         else { std::slice::from_raw_parts(host.indices.add(6 * first), 6 * cnt).to_vec() },
             }
         })
         .collect()

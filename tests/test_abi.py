@@ -160,3 +160,25 @@ def test_product_does_not_reference_the_oracle():
     import voxelphile_b200._lib as L
     deps = subprocess.run(["ldd", L.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in deps
+
+
+def test_rust_crates_and_integration_guide_agree_with_the_header():
+    """The Rust crates cannot be compiled here (no toolchain), so consistency of the text is the check there is:
+    vxp-sys declares exactly the functions of include/vxp.h with the same number of parameters, and every
+    `mesher.<method>(` the integration guide shows exists in the safe wrapper."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    c_decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(vxp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)}
+    sys_src = open(os.path.join(ROOT, "rust", "vxp-sys", "src", "lib.rs")).read()
+    r_decl = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (vxp_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]*)?;", sys_src, flags=re.S)}
+    assert set(r_decl) == set(c_decl) == set(declared_functions()), set(r_decl) ^ set(c_decl)
+
+    def arity(params):
+        params = params.strip()
+        return 0 if params in ("", "void") else params.count(",") + 1
+    for name in c_decl:
+        assert arity(c_decl[name]) == arity(r_decl[name]), name
+    wrapper = open(os.path.join(ROOT, "rust", "vxp", "src", "lib.rs")).read()
+    methods = set(re.findall(r"pub fn ([a-z_]+)\s*[(<]", wrapper))
+    guide = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    used = set(re.findall(r"\bmesher\.([a-z_]+)\(", guide)) | set(re.findall(r"\bMesher::([a-z_]+)\(", guide))
+    assert used and used <= methods, used - methods

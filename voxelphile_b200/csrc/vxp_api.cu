@@ -341,7 +341,10 @@ vxp_status column_scratch(vxp_ctx* ctx, uint32_t n, vxp::ColumnScratch* out) {
 // terrain fill: batches of at least this many chunks go through the shared column heights.  Measured on the 16^3 block
 // (4096 chunks, 16 per column): 60.1 us direct, 65.6 us through the columns - the fill kernel itself drops to ~50 us but
 // two memsets and two small kernels in front of it cost ~15 us, which only a larger batch amortises.
-constexpr uint32_t kColumnFillMin = 16384;
+#ifndef VXP_COLUMN_FILL_MIN
+#define VXP_COLUMN_FILL_MIN 16384
+#endif
+constexpr uint32_t kColumnFillMin = VXP_COLUMN_FILL_MIN;
 
 bool valid_mode(vxp_mode m) { return m == VXP_MODE_CULLED || m == VXP_MODE_GREEDY; }
 

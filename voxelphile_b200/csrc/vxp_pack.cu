@@ -41,37 +41,90 @@ __device__ __forceinline__ uint32_t palette_index(const uint32_t* pal, uint32_t 
 }
 }  // namespace
 
+// One CTA per chunk, two passes over its 64 KiB (the second one hits L2).
+// Pass 1 finds the chunk's distinct ids.  Block ids are small numbers in practice, so the set is first collected as a
+// 64-bit mask (bit v = id v occurs): a thread ORs its 128 voxels into two registers - one shift per voxel, one per group
+// of eight equal voxels - a warp reduction and two shared-memory atomics per warp merge them, and both the ascending
+// palette SPEC §10 asks for and every id's index in it fall out of the mask (rank of a bit = population count below it)
+// with no search at all.  A chunk with an id >= 64 takes the general path: an open-addressing set in shared memory, a
+// rank sort of its at most 16 values, a palette search per run of equal voxels.
+// Pass 2 turns 8 voxels into `bits` bytes.
 __global__ void __launch_bounds__(kThreads) pack_chunks_kernel(const uint16_t* __restrict__ voxels, uint32_t n,
                                                                 unsigned char* __restrict__ packed, unsigned long long capacity,
                                                                 unsigned long long* __restrict__ offsets,
                                                                 unsigned long long* __restrict__ cursor) {
     __shared__ PackShared sh;
-    const int tid = threadIdx.x;
+    __shared__ uint32_t s_mask[2], s_large;
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t chunk = blockIdx.x;
     if (chunk >= n) return;
     const uint4* src = reinterpret_cast<const uint4*>(voxels + (size_t)chunk * VXP_CHUNK_VOXELS);
     if (tid < kSetSlots) sh.set[tid] = kEmptySlot;
-    if (tid == 0) sh.distinct = 0;
+    if (tid == 0) { sh.distinct = 0; s_mask[0] = s_mask[1] = 0u; s_large = 0u; }
     __syncthreads();
-    // pass 1: the set of ids (a thread skips repeats of the value it inserted last: chunks are mostly runs)
-    uint32_t last = kEmptySlot;
-#pragma unroll 4
-    for (int k = 0; k < 16; ++k) {
-        const uint4 q = __ldg(src + tid + k * kThreads);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    // pass 1, small ids: the mask
+    {
+        uint32_t mlo = 0, mhi = 0, all = 0;
+        auto add = [&](uint32_t v) {
+            const uint32_t bit = 1u << (v & 31u);
+            if (v & 32u) mhi |= bit; else mlo |= bit;
+        };
+#pragma unroll 1
+        for (int k0 = 0; k0 < 16; k0 += 8) {                       // eight 16-byte loads in flight per thread (the pass is latency-bound otherwise)
+            uint4 qq[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t a = w[e] & 0xFFFFu, b = w[e] >> 16;
-            if (a != last) { set_insert(sh, a); last = a; }
-            if (b != last) { set_insert(sh, b); last = b; }
+            for (int k = 0; k < 8; ++k) qq[k] = __ldg(src + tid + (k0 + k) * kThreads);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint4 q = qq[k];
+                all |= q.x | q.y | q.z | q.w;
+                if (q.x == q.y && q.x == q.z && q.x == q.w && (q.x & 0xFFFFu) == (q.x >> 16)) {
+                    add(q.x & 0x3Fu);                              // eight equal voxels (ids >= 64 are caught by `all`)
+                } else {
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { add(w[e] & 0x3Fu); add((w[e] >> 16) & 0x3Fu); }
+                }
+            }
+        }
+        mlo = __reduce_or_sync(kFull, mlo);
+        mhi = __reduce_or_sync(kFull, mhi);
+        all = __reduce_or_sync(kFull, all);
+        if (lane == 0) {
+            if (mlo) atomicOr(&s_mask[0], mlo);
+            if (mhi) atomicOr(&s_mask[1], mhi);
+            if ((all | (all >> 16)) & 0xFFC0u) atomicOr(&s_large, 1u);
         }
     }
     __syncthreads();
-    const uint32_t distinct = sh.distinct;
-    const bool raw = distinct > 16u;
+    const uint32_t mlo = s_mask[0], mhi = s_mask[1];
+    const uint32_t plo = (uint32_t)__popc(mlo);
+    bool small = s_large == 0u && plo + (uint32_t)__popc(mhi) <= 16u;   // block-uniform
     if (tid < 16) sh.palette[tid] = 0;
+    if (!small) {
+        // general path: the set of ids (a thread skips repeats of the value it inserted last: chunks are mostly runs)
+        uint32_t last = kEmptySlot;
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            const uint4 q = __ldg(src + tid + k * kThreads);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t a = w[e] & 0xFFFFu, b = w[e] >> 16;
+                if (a != last) { set_insert(sh, a); last = a; }
+                if (b != last) { set_insert(sh, b); last = b; }
+            }
+        }
+    }
     __syncthreads();
-    if (!raw && tid < kSetSlots) {                                 // rank sort of at most 16 values
+    const uint32_t distinct = small ? plo + (uint32_t)__popc(mhi) : sh.distinct;
+    const bool raw = distinct > 16u;
+    if (small) {
+        if (tid < 64) {                                            // palette entry of rank r = the r-th set bit of the mask
+            const uint32_t m = tid < 32 ? mlo : mhi, below = m & ((1u << (tid & 31)) - 1u);
+            if ((m >> (tid & 31)) & 1u) sh.palette[(tid < 32 ? 0u : plo) + (uint32_t)__popc(below)] = (uint32_t)tid;
+        }
+    } else if (!raw && tid < kSetSlots) {                          // rank sort of at most 16 values
         const uint32_t v = sh.set[tid];
         if (v != kEmptySlot) {
             uint32_t rank = 0;
@@ -102,22 +155,34 @@ __global__ void __launch_bounds__(kThreads) pack_chunks_kernel(const uint16_t* _
     if (tid < 8) reinterpret_cast<uint32_t*>(rec + 16)[tid] = sh.palette[2 * tid] | sh.palette[2 * tid + 1] << 16;
     if (bits == 0u) return;
     unsigned char* data = rec + kHeaderBytes;
+    // index of id v in the palette: small ids: the number of mask bits below bit v
+    auto index_of = [&](uint32_t v) -> uint32_t {
+        if (small) return ((v & 32u) ? plo : 0u) + (uint32_t)__popc(((v & 32u) ? mhi : mlo) & ((1u << (v & 31u)) - 1u));
+        return palette_index(sh.palette, len, v);
+    };
+    const uint32_t spread = bits == 1u ? 0xFFu : bits == 2u ? 0x5555u : 0x11111111u;
     // pass 2 (L2 hits): 8 voxels -> 8 indices -> `bits` bytes
-    for (int k = 0; k < 16; ++k) {
-        const int j = tid + k * kThreads;
-        const uint4 q = __ldg(src + j);
+#pragma unroll 1
+    for (int k0 = 0; k0 < 16; k0 += 4) {
+    uint4 qq[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) qq[k] = __ldg(src + tid + (k0 + k) * kThreads);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = tid + (k0 + k) * kThreads;
+        const uint4 q = qq[k];
         if (bits == 16u) { reinterpret_cast<uint4*>(data)[j] = q; continue; }
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
         uint32_t out = 0;
         // chunks are mostly runs of one id: look an id up only when it differs from the previous voxel's
-        uint32_t lastv = w[0] & 0xFFFFu, lasti = palette_index(sh.palette, len, lastv);
+        uint32_t lastv = w[0] & 0xFFFFu, lasti = index_of(lastv);
         if (q.x == q.y && q.x == q.z && q.x == q.w && lastv == (q.x >> 16)) {   // eight equal voxels: one look-up, one multiply
-            out = lasti * (bits == 1u ? 0xFFu : bits == 2u ? 0x5555u : 0x11111111u);
+            out = lasti * spread;
         } else {
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                const uint32_t v = (t & 1) ? w[t >> 1] >> 16 : w[t >> 1] & 0xFFFFu;
-                if (v != lastv) { lastv = v; lasti = palette_index(sh.palette, len, v); }
+                const uint32_t v = (w[t >> 1] >> (16 * (t & 1))) & 0xFFFFu;
+                if (v != lastv) { lastv = v; lasti = index_of(v); }
                 out |= lasti << (bits * t);
             }
         }
@@ -125,71 +190,91 @@ __global__ void __launch_bounds__(kThreads) pack_chunks_kernel(const uint16_t* _
         else if (bits == 2u) reinterpret_cast<unsigned short*>(data)[j] = (unsigned short)out;
         else reinterpret_cast<uint32_t*>(data)[j] = out;
     }
+    }
 }
 
 // status[0] is set to 1 if any record is malformed (offset outside the buffer - vxp_pack_chunks marks records that did
 // not fit with ~0 -, misaligned, bad magic / bits / palette length, data running past the end); such chunks come out as air.
-__global__ void __launch_bounds__(kThreads) unpack_chunks_kernel(const unsigned char* __restrict__ packed, unsigned long long packed_bytes,
-                                                                  const unsigned long long* __restrict__ offsets, uint32_t n,
-                                                                  uint16_t* __restrict__ voxels, uint32_t* __restrict__ status) {
-    __shared__ uint32_t s_pal[16];
-    __shared__ uint32_t s_bits;
+// One CTA per chunk, eight CTAs per SM: offset -> header -> data is a chain of three dependent global round trips in front
+// of 64 KiB of stores, which only other resident chunks can hide.  Every thread reads and validates the header itself
+// (the same words for all of them: one broadcast load, no shared-memory round for it); only the palette goes through
+// shared memory.  (Persistent CTAs prefetching the next record's header were measured slower, 78 us against 71 us per
+// 4096 chunks: records cost between 16 stores and a full decode, and a static stride over the batch balances them badly.)
+struct UnpackHead {
+    unsigned long long off;
+    uint32_t h0, h1, h2, pal;   // magic, bits | len << 16, data bytes, palette word (threads 0..7)
+    bool in_buffer;
+};
+__device__ __forceinline__ UnpackHead unpack_fetch(const unsigned char* __restrict__ packed, unsigned long long packed_bytes,
+                                                   const unsigned long long* __restrict__ offsets, uint32_t chunk, uint32_t n) {
+    UnpackHead u{};
+    if (chunk >= n) return u;
+    u.off = __ldg(offsets + chunk);
+    u.in_buffer = (u.off & 15ull) == 0ull && u.off <= packed_bytes && packed_bytes - u.off >= (unsigned long long)kHeaderBytes;
+    if (u.in_buffer) {
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(packed + u.off);
+        u.h0 = __ldg(h);
+        u.h1 = __ldg(h + 1);
+        u.h2 = __ldg(h + 2);
+        if (threadIdx.x < 8) u.pal = __ldg(h + 4 + threadIdx.x);
+    }
+    return u;
+}
+__global__ void __launch_bounds__(kThreads, 8) unpack_chunks_kernel(const unsigned char* __restrict__ packed, unsigned long long packed_bytes,
+                                                                     const unsigned long long* __restrict__ offsets, uint32_t n,
+                                                                     uint16_t* __restrict__ voxels, uint32_t* __restrict__ status) {
+    __shared__ uint32_t s_pal[1][16];
     const int tid = threadIdx.x;
     const uint32_t chunk = blockIdx.x;
     if (chunk >= n) return;
-    const unsigned long long off = offsets[chunk];
-    const bool in_buffer = (off & 15ull) == 0ull && off <= packed_bytes && packed_bytes - off >= (unsigned long long)kHeaderBytes;   // block-uniform
-    const unsigned char* rec = packed + (in_buffer ? off : 0ull);
-    if (tid == 0) {
-        bool ok = in_buffer;
-        uint32_t bits = 0;
-        if (ok) {
-            const uint32_t* h = reinterpret_cast<const uint32_t*>(rec);
-            bits = h[1] & 0xFFFFu;
-            const uint32_t len = h[1] >> 16;
-            ok = h[0] == kMagic && (bits == 0u || bits == 1u || bits == 2u || bits == 4u || bits == 16u) &&
-                 h[2] == 4096u * bits && (bits == 16u ? len == 0u : (len >= 1u && len <= 16u && len <= (1u << bits))) &&
-                 packed_bytes - off - (unsigned long long)kHeaderBytes >= (unsigned long long)h[2];
+    const UnpackHead cur = unpack_fetch(packed, packed_bytes, offsets, chunk, n);
+    constexpr int buf = 0;
+    {
+        // every thread validates the header it read itself (the same words for all of them): no broadcast, no barrier for it
+        uint32_t bits = cur.h1 & 0xFFFFu;
+        const uint32_t len = cur.h1 >> 16;
+        const bool ok = cur.in_buffer && cur.h0 == kMagic && (bits == 0u || bits == 1u || bits == 2u || bits == 4u || bits == 16u) &&
+                        cur.h2 == 4096u * bits && (bits == 16u ? len == 0u : (len >= 1u && len <= 16u && len <= (1u << bits))) &&
+                        packed_bytes - cur.off - (unsigned long long)kHeaderBytes >= (unsigned long long)cur.h2;
+        if (!ok) {
+            if (tid == 0) atomicExch(status, 1u);
+            bits = 0xFFu;
         }
-        if (!ok) atomicExch(status, 1u);
-        s_bits = ok ? bits : 0xFFu;
-    }
-    if (tid < 8 && in_buffer) {
-        const uint32_t p = reinterpret_cast<const uint32_t*>(rec + 16)[tid];
-        s_pal[2 * tid] = p & 0xFFFFu;
-        s_pal[2 * tid + 1] = p >> 16;
-    }
-    __syncthreads();
-    const uint32_t bits = s_bits;
-    uint4* dst = reinterpret_cast<uint4*>(voxels + (size_t)chunk * VXP_CHUNK_VOXELS);
-    const unsigned char* data = rec + kHeaderBytes;
-    if (bits == 0u || bits == 0xFFu) {
-        const uint32_t b = bits == 0u ? s_pal[0] : 0u, bb = b | b << 16;
-        for (int k = 0; k < 16; ++k) dst[tid + k * kThreads] = make_uint4(bb, bb, bb, bb);
-        return;
-    }
-    if (bits == 16u) {
+        if (tid < 8) {
+            s_pal[buf][2 * tid] = cur.pal & 0xFFFFu;
+            s_pal[buf][2 * tid + 1] = cur.pal >> 16;
+        }
+        __syncthreads();                                       // palette published
+        const uint32_t* pal = s_pal[buf];
+        uint4* dst = reinterpret_cast<uint4*>(voxels + (size_t)chunk * VXP_CHUNK_VOXELS);
+        const unsigned char* data = packed + (ok ? cur.off : 0ull) + kHeaderBytes;
+        if (bits == 0u || bits == 0xFFu) {
+            const uint32_t b = bits == 0u ? pal[0] : 0u, bb = b | b << 16;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) dst[tid + k * kThreads] = make_uint4(bb, bb, bb, bb);
+        } else if (bits == 16u) {
 #pragma unroll 8
-        for (int k = 0; k < 16; ++k) dst[tid + k * kThreads] = __ldg(reinterpret_cast<const uint4*>(data) + tid + k * kThreads);
-        return;
-    }
-    const uint32_t mask = (1u << bits) - 1u;
+            for (int k = 0; k < 16; ++k) dst[tid + k * kThreads] = __ldg(reinterpret_cast<const uint4*>(data) + tid + k * kThreads);
+        } else {
+            const uint32_t mask = (1u << bits) - 1u;
 #pragma unroll 1
-    for (int k0 = 0; k0 < 16; k0 += 8) {                  // eight loads in flight per thread, then eight stores
-        uint32_t in[8];
+            for (int k0 = 0; k0 < 16; k0 += 8) {                  // eight loads in flight per thread, then eight stores
+                uint32_t in[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int j = tid + (k0 + k) * kThreads;
-            in[k] = bits == 1u ? data[j] : bits == 2u ? reinterpret_cast<const unsigned short*>(data)[j]
-                                                      : reinterpret_cast<const uint32_t*>(data)[j];
-        }
+                for (int k = 0; k < 8; ++k) {
+                    const int j = tid + (k0 + k) * kThreads;
+                    in[k] = bits == 1u ? data[j] : bits == 2u ? reinterpret_cast<const unsigned short*>(data)[j]
+                                                              : reinterpret_cast<const uint32_t*>(data)[j];
+                }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint32_t w[4];
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                w[e] = s_pal[(in[k] >> (bits * (2 * e))) & mask] | s_pal[(in[k] >> (bits * (2 * e + 1))) & mask] << 16;
-            dst[tid + (k0 + k) * kThreads] = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int e = 0; e < 4; ++e)
+                        w[e] = pal[(in[k] >> (bits * (2 * e))) & mask] | pal[(in[k] >> (bits * (2 * e + 1))) & mask] << 16;
+                    dst[tid + (k0 + k) * kThreads] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
         }
     }
 }
@@ -213,8 +298,9 @@ cudaError_t launch_unpack_chunks(const unsigned char* d_packed, unsigned long lo
 }  // namespace vxp
 
 // ====================================================================== LOD (SPEC §11)
-// One output chunk = 2 x 2 x 2 stored chunks at half resolution.  One CTA per output chunk; a thread produces 8
-// output voxels (one 16-byte store) from 4 rows x 16 input voxels.  HBM-bound: 8 bytes read per byte written.
+// One output chunk = 2 x 2 x 2 stored chunks at half resolution.  Four CTAs per output chunk (a quarter of its z-layers
+// each: a grid of whole output chunks is a few hundred CTAs for a typical batch, less than one even wave); a thread
+// produces 8 output voxels (one 16-byte store) from 4 rows x 16 input voxels.  HBM-bound: 8 bytes read per byte written.
 namespace vxp {
 namespace {
 // first non-air of (a, b) per u16 lane pair -> one u16: a if a != 0 else b
@@ -224,13 +310,13 @@ __device__ __forceinline__ uint32_t first_solid(uint32_t a, uint32_t b) { return
 __global__ void __launch_bounds__(kThreads) downsample_chunks_kernel(const uint16_t* __restrict__ voxels,
                                                                       const int32_t* __restrict__ child8, uint32_t n_out,
                                                                       uint16_t* __restrict__ out) {
-    const uint32_t oc = blockIdx.x;
+    const uint32_t oc = blockIdx.x >> 2, part = blockIdx.x & 3u;
     if (oc >= n_out) return;
     __shared__ int s_child[8];
     if (threadIdx.x < 8) s_child[threadIdx.x] = child8[8 * (size_t)oc + threadIdx.x];
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)oc * VXP_CHUNK_VOXELS);
-    for (int j = threadIdx.x; j < 4096; j += kThreads) {          // j = (z*32 + y)*4 + p
+    for (int j = part * 1024 + threadIdx.x; j < (int)(part + 1) * 1024; j += kThreads) {   // j = (z*32 + y)*4 + p
         const int z = j >> 7, y = (j >> 2) & 31, p = j & 3;        // output voxels x = 8p .. 8p+7
         const int c = (p >> 1) | (y >> 4) << 1 | (z >> 4) << 2;    // child: dx + 2 dy + 4 dz
         const int ch = s_child[c];
@@ -261,7 +347,7 @@ __global__ void __launch_bounds__(kThreads) downsample_chunks_kernel(const uint1
 cudaError_t launch_downsample_chunks(const uint16_t* d_voxels, const int32_t* d_child8, uint32_t n_out, uint16_t* d_out,
                                      cudaStream_t stream) {
     if (n_out == 0) return cudaSuccess;
-    downsample_chunks_kernel<<<n_out, kThreads, 0, stream>>>(d_voxels, d_child8, n_out, d_out);
+    downsample_chunks_kernel<<<4 * n_out, kThreads, 0, stream>>>(d_voxels, d_child8, n_out, d_out);
     return cudaGetLastError();
 }
 }  // namespace vxp
