@@ -159,7 +159,8 @@ vxp_status vxp_pack_chunks(vxp_ctx *ctx, const uint16_t *d_voxels, uint32_t n, u
                            uint64_t capacity_bytes, uint64_t *d_offsets, uint64_t *d_total_bytes);
 /* Expand n records of the packed buffer (packed_bytes long) into d_voxels (n * 32768 u16).  Malformed records - bad
  * header, or an offset or data that does not lie inside the buffer, such as the UINT64_MAX vxp_pack_chunks gives a
- * record that did not fit - come out as air and make the NEXT vxp_ctx_synchronize return VXP_ERR_BAD_ARG. */
+ * record that did not fit - come out as air and make the NEXT vxp_ctx_synchronize return VXP_ERR_BAD_ARG (calls queue
+ * without synchronising; the verdict covers every vxp_unpack_chunks call since the previous synchronize). */
 vxp_status vxp_unpack_chunks(vxp_ctx *ctx, const uint8_t *d_packed, uint64_t packed_bytes, const uint64_t *d_offsets,
                              uint32_t n, uint16_t *d_voxels);
 

@@ -624,6 +624,13 @@ def test_unpack_accepts_any_palette_order_and_rejects_malformed(mesher):
         mesher.synchronize()
     assert e.value.kind == "BadArg"
     mesher.synchronize()                                       # the verdict is reported once
+    # calls queue without a synchronisation between them; a malformed record in any of them fails the next synchronize
+    d_bad, d_ok, zero = dev(bad), dev(buf), dev(np.zeros(1, np.int64))
+    mesher.unpack(d_ok, zero); mesher.unpack(d_bad, zero); last = mesher.unpack(d_ok, zero)
+    with pytest.raises(MeshError):
+        mesher.synchronize()
+    assert np.array_equal(last.cpu().numpy().view(np.uint16).reshape(-1), vox)
+    mesher.unpack(d_ok, zero); mesher.synchronize()
     with pytest.raises(MeshError):
         mesher.mesh_packed_host(bad, np.zeros(1, np.uint64), None, 1)
     # offsets that do not lie inside the buffer - the UINT64_MAX that vxp_pack_chunks gives a record that did not fit,

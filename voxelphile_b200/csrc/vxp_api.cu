@@ -440,6 +440,7 @@ vxp_status vxp_ctx_create(int device, vxp_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_dirty_count), sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_dirty_count), sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_status), sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_total), sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_totals), vxp_ctx::kMaxSlices * sizeof(uint64_t));
@@ -534,17 +535,24 @@ vxp_status vxp_ctx_set_host_indices(vxp_ctx* ctx, int enabled) {
     return VXP_OK;
 }
 
+// The stream is idle: did an unpack since the last look meet a malformed record?  The device word is sticky (set by the
+// kernels, never cleared by a launch), so any number of unpack calls may be queued without a synchronisation between them.
+static vxp_status unpack_verdict(vxp_ctx* ctx) {
+    if (!ctx->status_pending) return VXP_OK;
+    ctx->status_pending = false;
+    VXP_CUDA(ctx, cudaMemcpy(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (*ctx->h_status == 0u) return VXP_OK;
+    VXP_CUDA(ctx, cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
+    ctx->last_error = "vxp_unpack_chunks: malformed record";
+    return VXP_ERR_BAD_ARG;
+}
+
 vxp_status vxp_ctx_synchronize(vxp_ctx* ctx) {
     if (!ctx) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->chain_open = false;
-    if (ctx->status_pending) {           // a vxp_unpack_chunks call since the last synchronize: did it meet a malformed record?
-        ctx->status_pending = false;
-        VXP_CUDA(ctx, cudaMemcpy(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        if (*ctx->h_status) return VXP_ERR_BAD_ARG;
-    }
-    return VXP_OK;
+    return unpack_verdict(ctx);
 }
 
 const char* vxp_last_error(const vxp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
@@ -741,11 +749,6 @@ vxp_status vxp_unpack_chunks(vxp_ctx* ctx, const uint8_t* d_packed, uint64_t pac
     if (!ctx || (n && (!d_packed || !aligned16(d_packed) || !d_offsets || !d_voxels || !aligned16(d_voxels)))) return VXP_ERR_BAD_ARG;
     DeviceGuard g(ctx->device);
     ctx->chain_open = false;
-    if (ctx->status_pending) {           // keep an earlier call's verdict: fold it in before the word is zeroed again
-        VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        VXP_CUDA(ctx, cudaMemcpy(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        if (*ctx->h_status) { ctx->status_pending = false; return VXP_ERR_BAD_ARG; }
-    }
     VXP_CUDA(ctx, vxp::launch_unpack_chunks(d_packed, packed_bytes, reinterpret_cast<const unsigned long long*>(d_offsets), n, d_voxels,
                                             ctx->d_status, ctx->stream));
     ctx->launches += n ? 1 : 0;
@@ -965,7 +968,7 @@ vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t pa
     if ((s = grow_device(ctx, &ctx->d_packed, &ctx->packed_cap, (size_t)packed_bytes + 16, 1)) != VXP_OK) return s;
     if ((s = grow_device(ctx, &ctx->d_offsets, &ctx->offsets_cap, n_stored, 1)) != VXP_OK) return s;
     if ((s = join_chain(ctx)) != VXP_OK) return s;
-    if (ctx->status_pending && (s = vxp_ctx_synchronize(ctx)) != VXP_OK) return s;   // an earlier vxp_unpack_chunks verdict is not lost
+    if (ctx->status_pending && (s = vxp_ctx_synchronize(ctx)) != VXP_OK) return s;   // an earlier vxp_unpack_chunks verdict stays that call's
     const int32_t* d_nbr = nbr6 ? ctx->d_nbr6 : nullptr;
     if (n_stored) {
         if ((s = upload(ctx, ctx->d_packed, packed, packed_bytes, ctx->stream)) != VXP_OK) return s;
@@ -973,6 +976,7 @@ vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t pa
         if (nbr6) VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr6, nbr6, (size_t)n * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         VXP_CUDA(ctx, vxp::launch_unpack_chunks(ctx->d_packed, packed_bytes, ctx->d_offsets, n_stored, ctx->d_voxels, ctx->d_status, ctx->stream));
         ctx->launches += 1;
+        ctx->status_pending = true;
     }
     const int greedy = mode == VXP_MODE_GREEDY;
     s = mesh_into_host(
@@ -981,6 +985,7 @@ vxp_status vxp_mesh_packed_host(vxp_ctx* ctx, const uint8_t* packed, uint64_t pa
             return chained_mesh_launch(ctx, ctx->d_voxels, d_nbr, n, greedy, dev) == VXP_OK ? cudaSuccess : cudaErrorUnknown;
         },
         out);
+    if (s == VXP_OK) s = unpack_verdict(ctx);      // mesh_into_host has synchronised: a malformed record fails the call
     if (s == VXP_OK) {
         ctx->world_n = n;
         ctx->world_stored = n_stored;

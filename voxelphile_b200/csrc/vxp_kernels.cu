@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kThreads) terrain_fill_kernel(const vxp_coord*
                 for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
                 v = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            dst[j] = v;
+            st_voxels16(dst + j, v);
         }
         __syncthreads();
     }
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) terrain_fill_columns_kernel(const vx
             for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
             v = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        dst[j] = v;
+        st_voxels16(dst + j, v);
     }
 }
 

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 8) unpack_chunks_kernel(const unsign
     __shared__ uint32_t s_pal[1][16];
     const int tid = threadIdx.x;
     const uint32_t chunk = blockIdx.x;
+    constexpr int kPer = 16;                                       // 16-byte stores per thread
     if (chunk >= n) return;
     const UnpackHead cur = unpack_fetch(packed, packed_bytes, offsets, chunk, n);
     constexpr int buf = 0;
@@ -250,29 +251,30 @@ __global__ void __launch_bounds__(kThreads, 8) unpack_chunks_kernel(const unsign
         const unsigned char* data = packed + (ok ? cur.off : 0ull) + kHeaderBytes;
         if (bits == 0u || bits == 0xFFu) {
             const uint32_t b = bits == 0u ? pal[0] : 0u, bb = b | b << 16;
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) dst[tid + k * kThreads] = make_uint4(bb, bb, bb, bb);
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) st_voxels16(dst + tid + k * kThreads, make_uint4(bb, bb, bb, bb));
         } else if (bits == 16u) {
-#pragma unroll 8
-            for (int k = 0; k < 16; ++k) dst[tid + k * kThreads] = __ldg(reinterpret_cast<const uint4*>(data) + tid + k * kThreads);
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) st_voxels16(dst + tid + k * kThreads, __ldg(reinterpret_cast<const uint4*>(data) + tid + k * kThreads));
         } else {
             const uint32_t mask = (1u << bits) - 1u;
+            constexpr int kFlight = 8;                             // loads in flight per thread, then as many stores
 #pragma unroll 1
-            for (int k0 = 0; k0 < 16; k0 += 8) {                  // eight loads in flight per thread, then eight stores
-                uint32_t in[8];
+            for (int k0 = 0; k0 < kPer; k0 += kFlight) {
+                uint32_t in[kFlight];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < kFlight; ++k) {
                     const int j = tid + (k0 + k) * kThreads;
                     in[k] = bits == 1u ? data[j] : bits == 2u ? reinterpret_cast<const unsigned short*>(data)[j]
                                                               : reinterpret_cast<const uint32_t*>(data)[j];
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < kFlight; ++k) {
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         w[e] = pal[(in[k] >> (bits * (2 * e))) & mask] | pal[(in[k] >> (bits * (2 * e + 1))) & mask] << 16;
-                    dst[tid + (k0 + k) * kThreads] = make_uint4(w[0], w[1], w[2], w[3]);
+                    st_voxels16(dst + tid + (k0 + k) * kThreads, make_uint4(w[0], w[1], w[2], w[3]));
                 }
             }
         }
@@ -289,8 +291,7 @@ cudaError_t launch_pack_chunks(const uint16_t* d_voxels, uint32_t n, unsigned ch
 
 cudaError_t launch_unpack_chunks(const unsigned char* d_packed, unsigned long long packed_bytes, const unsigned long long* d_offsets,
                                  uint32_t n, uint16_t* d_voxels, uint32_t* d_status, cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(d_status, 0, sizeof(uint32_t), stream);
-    if (e != cudaSuccess || n == 0) return e;
+    if (n == 0) return cudaSuccess;                    // d_status is sticky: the caller clears it when it has read a verdict
     unpack_chunks_kernel<<<n, kThreads, 0, stream>>>(d_packed, packed_bytes, d_offsets, n, d_voxels, d_status);
     return cudaGetLastError();
 }
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kThreads) downsample_chunks_kernel(const uint1
             }
             r = make_uint4(o[0] | o[1] << 16, o[2] | o[3] << 16, o[4] | o[5] << 16, o[6] | o[7] << 16);
         }
-        dst[j] = r;
+        st_voxels16(dst + j, r);
     }
 }
 
