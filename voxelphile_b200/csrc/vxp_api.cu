@@ -88,7 +88,7 @@ struct vxp_ctx {
     // Two launch slots used alternately, so that consecutive launches share nothing (launch chaining, vxp_mesh_common.cuh).
     uint32_t* d_tags[2] = {};       unsigned long long* d_planes[2] = {};    size_t bnd_cap = 0;   // chunks
     uint32_t epoch = 0;
-    unsigned long long* d_counters = nullptr;   // one zero-initialised launch counter per slot
+    unsigned long long* d_counters = nullptr;   // one zero-initialised launch counter per slot, [2]: the pack kernel's byte cursor
     int slot = 0;
     int overlap = 0;                            // vxp_ctx_set_overlap
     int host_indices = 1;                       // vxp_ctx_set_host_indices
@@ -434,8 +434,8 @@ vxp_status vxp_ctx_create(int device, vxp_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = vxp::configure_device();
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_total), sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 2 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, 3 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_dirty_count), sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_dirty_count), sizeof(uint32_t));
@@ -739,7 +739,7 @@ vxp_status vxp_pack_chunks(vxp_ctx* ctx, const uint16_t* d_voxels, uint32_t n, u
     DeviceGuard g(ctx->device);
     ctx->chain_open = false;
     VXP_CUDA(ctx, vxp::launch_pack_chunks(d_voxels, n, d_packed, capacity_bytes, reinterpret_cast<unsigned long long*>(d_offsets),
-                                          reinterpret_cast<unsigned long long*>(d_total_bytes), ctx->stream));
+                                          reinterpret_cast<unsigned long long*>(d_total_bytes), ctx->d_counters + 2, ctx->stream));
     ctx->launches += n ? 1 : 0;
     return VXP_OK;
 }

@@ -68,10 +68,12 @@ cudaError_t launch_apply_edits(uint16_t* d_voxels, const int32_t* d_nbr6, uint32
 cudaError_t launch_mesh_list(const uint16_t* d_voxels, const int32_t* d_nbr6, uint32_t n, const uint32_t* d_list,
                              const uint32_t* d_count, uint32_t max_count, int greedy, const vxp_mesh_dev& out,
                              unsigned long long* counter, cudaStream_t stream);
-// Chunk wire format (SPEC §10; vxp_pack.cu).  d_total: one 8-byte cursor, zeroed here, ends as the bytes
-// the batch needs (records that do not fit get offset ~0).  d_status: one word, zeroed here, 1 = malformed record.
+// Chunk wire format (SPEC §10; vxp_pack.cu).  d_total ends as the bytes the batch needs (records that do
+// not fit get offset ~0); d_cursor: 8 bytes of context scratch, zero between launches (the kernel leaves it so).
+// d_status: one sticky word, 1 = malformed record (the caller clears it when it has read a verdict).
 cudaError_t launch_pack_chunks(const uint16_t* d_voxels, uint32_t n, unsigned char* d_packed, unsigned long long capacity,
-                               unsigned long long* d_offsets, unsigned long long* d_total, cudaStream_t stream);
+                               unsigned long long* d_offsets, unsigned long long* d_total, unsigned long long* d_cursor,
+                               cudaStream_t stream);
 cudaError_t launch_unpack_chunks(const unsigned char* d_packed, unsigned long long packed_bytes, const unsigned long long* d_offsets,
                                  uint32_t n, uint16_t* d_voxels, uint32_t* d_status, cudaStream_t stream);
 // LOD (SPEC §11): out[i] = half-resolution chunk of the 2x2x2 stored chunks child8[i][dx + 2 dy + 4 dz] (-1 = air).

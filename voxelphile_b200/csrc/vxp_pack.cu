@@ -11,6 +11,7 @@ namespace {
 constexpr uint32_t kMagic = 0x31505856u;      // "VXP1"
 constexpr int kHeaderBytes = 48;              // 16-byte header + 16-entry palette
 constexpr int kSetSlots = 64;
+constexpr int kCursorBits = 42;                // byte cursor of a pack launch: 4 TiB, 2^22 chunks
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 
 struct PackShared {
@@ -52,7 +53,8 @@ __device__ __forceinline__ uint32_t palette_index(const uint32_t* pal, uint32_t 
 __global__ void __launch_bounds__(kThreads) pack_chunks_kernel(const uint16_t* __restrict__ voxels, uint32_t n,
                                                                 unsigned char* __restrict__ packed, unsigned long long capacity,
                                                                 unsigned long long* __restrict__ offsets,
-                                                                unsigned long long* __restrict__ cursor) {
+                                                                unsigned long long* __restrict__ cursor,
+                                                                unsigned long long* __restrict__ total) {
     __shared__ PackShared sh;
     __shared__ uint32_t s_mask[2], s_large;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -135,14 +137,21 @@ __global__ void __launch_bounds__(kThreads) pack_chunks_kernel(const uint16_t* _
     if (tid == 0) {
         const uint32_t bits = raw ? 16u : distinct <= 1u ? 0u : distinct <= 2u ? 1u : distinct <= 4u ? 2u : 4u;
         const unsigned long long size = kHeaderBytes + 4096ull * bits;
-        const unsigned long long off = atomicAdd(cursor, size);
+        // one atomic per chunk reserves the record and checks the CTA in (count above bit 42): the last one to reserve
+        // knows the batch's size, hands it to the caller and leaves the cursor zeroed - no memset in front of the launch
+        const unsigned long long old = atomicAdd(cursor, size | 1ull << kCursorBits);
+        const unsigned long long off = old & ((1ull << kCursorBits) - 1ull);
+        if ((old >> kCursorBits) == n - 1u) {
+            *total = off + size;
+            *cursor = 0ull;
+        }
         sh.bits = bits;
         sh.len = raw ? 0u : distinct;
         sh.offset = off + size <= capacity ? off : ~0ull;
         offsets[chunk] = sh.offset;
     }
     __syncthreads();
-    if (sh.offset == ~0ull) return;                                // does not fit: *cursor tells the caller how much is needed
+    if (sh.offset == ~0ull) return;                                // does not fit: *total tells the caller how much is needed
     unsigned char* rec = packed + sh.offset;
     const uint32_t bits = sh.bits, len = sh.len;
     if (tid == 0) {
@@ -282,10 +291,11 @@ __global__ void __launch_bounds__(kThreads, 8) unpack_chunks_kernel(const unsign
 }
 
 cudaError_t launch_pack_chunks(const uint16_t* d_voxels, uint32_t n, unsigned char* d_packed, unsigned long long capacity,
-                               unsigned long long* d_offsets, unsigned long long* d_total, cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), stream);
-    if (e != cudaSuccess || n == 0) return e;
-    pack_chunks_kernel<<<n, kThreads, 0, stream>>>(d_voxels, n, d_packed, capacity, d_offsets, d_total);
+                               unsigned long long* d_offsets, unsigned long long* d_total, unsigned long long* d_cursor,
+                               cudaStream_t stream) {
+    if (n == 0) return cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), stream);
+    if (n > (1u << 22)) return cudaErrorInvalidValue;
+    pack_chunks_kernel<<<n, kThreads, 0, stream>>>(d_voxels, n, d_packed, capacity, d_offsets, d_cursor, d_total);
     return cudaGetLastError();
 }
 
