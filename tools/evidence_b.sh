@@ -1,8 +1,10 @@
 #!/bin/bash
 # GPU box, 1 GPU: one `ncu --set full` capture per kernel (two launches each, after the fills), exported as raw/source CSV.
-# usage: tools/evidence_b.sh TAG
-tag=$1; o=gpurun_out
+# usage: tools/evidence_b.sh TAG [kernel ...]   (kernels: greedy culled fused fill pack unpack lod; default all)
+tag=$1; shift; o=gpurun_out
+want=" ${*:-greedy culled fused fill pack unpack lod} "
 cap() {  # name target regex
+  case "$want" in *" $1 "*) ;; *) return;; esac
   python tools/ncu_target.py $2 6 > $o/${tag}_$1.run 2>&1 || return
   ncu --set full --clock-control none --import-source on -k regex:$3 -s 2 -c 2 -f -o $o/${tag}_$1 python tools/ncu_target.py $2 6 > $o/${tag}_$1.ncu.log 2>&1
   ncu -i $o/${tag}_$1.ncu-rep --page raw --csv > $o/${tag}_$1_raw.csv 2>/dev/null
