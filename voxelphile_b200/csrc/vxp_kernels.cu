@@ -226,46 +226,110 @@ __global__ void __launch_bounds__(kThreads) terrain_fill_columns_kernel(const vx
     }
 }
 
-// ---- one surface chunk: footprint -> voxels, one 16 KiB slab at a time into the ring -> the pipeline of vxp_mesh.cuh
-// halo occupancy straight from the heights (solid iff Y <= h); s_h[(z+1)*34 + (x+1)]
-__device__ __forceinline__ void halo_from_heights(uint32_t* occ, uint32_t (*xh)[32], const short* s_h, int Y0) {
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 128; i += kThreads) {       // Y and Z halo rows: word over x
-        const int face = i >> 5, r = i & 31;          // 0:-Y 1:+Y 2:-Z 3:+Z
-        int zz, Y, dst;
-        if (face == 0) { zz = r; Y = Y0 - 1; dst = (r + 1) * 34 + 0; }
-        else if (face == 1) { zz = r; Y = Y0 + 32; dst = (r + 1) * 34 + 33; }
-        else if (face == 2) { zz = -1; Y = Y0 + r; dst = 0 * 34 + (r + 1); }
-        else { zz = 32; Y = Y0 + r; dst = 33 * 34 + (r + 1); }
-        const short* hp = s_h + (zz + 1) * 34 + 1;
-        uint32_t bits = 0;
-#pragma unroll 8
-        for (int x = 0; x < 32; ++x) bits |= (uint32_t)(Y <= hp[x]) << x;
-        occ[dst] = bits;
-    }
-    if (tid < 64) {                                   // X halos: word over y for each z
-        const int face = tid >> 5, z = tid & 31;
-        const int h = s_h[(z + 1) * 34 + (face ? 33 : 0)];
-        uint32_t bits = 0;
-#pragma unroll 8
-        for (int y = 0; y < 32; ++y) bits |= (uint32_t)(Y0 + y <= h) << y;
-        xh[face][z] = bits;
-    }
+// ---- one surface chunk: footprint -> occupancy / equality words, no voxels in between.
+// A terrain column (x, z) is a function of y alone: solid up to its height, grass on top, three layers of dirt, then stone
+// and slate in bands of eight.  So the 32 voxels of a column are four words with bit y set - occupancy and the three id
+// bit planes - and each is a handful of shifts (where the unfused path writes, reads back and converts 32 voxels).
+// Words over y are what the X planes want as they are (face masks: the lanes next door; equality along y: a shift); the
+// Y / Z planes want words over x, which 32 x 32 bit transposes across the warp deliver.  s_h[(z+1)*34 + (x+1)].
+__device__ __forceinline__ uint32_t bits_le(int n) {                // bits 0..n of a word (none for n < 0, all for n >= 31)
+    const int m = min(max(n + 1, 0), 32);
+    return m == 32 ? kFull : (1u << m) - 1u;
 }
-__device__ __forceinline__ void generate_slab(unsigned char* slab, const short* s_h, int Y0, int s) {
-    uint4* slab4 = reinterpret_cast<uint4*>(slab);
-    const int tid = threadIdx.x;
-#pragma unroll 2
-    for (int k = 0; k < 4; ++k) {
-        const int j = s * 1024 + tid + k * kThreads;      // uint4 index inside the chunk: (z*32 + y)*4 + piece
-        const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
-        const short* hp = s_h + (z + 1) * 34 + x0 + 1;
-        uint32_t w[4];
+struct ColumnWords {
+    uint32_t occ, p0, p1, p2;                                        // bit y: voxel solid / bit b of its block id
+};
+// t = height of the column relative to the chunk's first layer (the chunk's Y0 is a multiple of 32, so the slate bands
+// (Y >> 3) & 1 are the same bits in every chunk); same blocks as terrain_block()
+__device__ __forceinline__ ColumnWords column_words(int t) {
+    constexpr uint32_t kSlate = 0xFF00FF00u;
+    ColumnWords c;
+    c.occ = bits_le(t);
+    const uint32_t below = bits_le(t - 1), deep = bits_le(t - 4);
+    const uint32_t grass = c.occ & ~below, dirt = below & ~deep, stone = deep & ~kSlate;   // ids 1, 2, 3; slate = 4
+    c.p0 = grass | stone;
+    c.p1 = dirt | stone;
+    c.p2 = deep & kSlate;
+    return c;
+}
+// Z halo layers (z = -1, 32) of the occupancy: one transpose each, warps 0 and 1
+template <class SM>
+__device__ __forceinline__ void z_halo_from_heights(SM& sm, const short* s_h, int Y0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= 2) return;
+    const int zz = warp ? 33 : 0;                                     // row of the footprint
+    uint32_t w[1] = {bits_le(s_h[zz * 34 + lane + 1] - Y0)};
+    transpose32xN(w, lane);
+    sm.occ[zz * 34 + lane + 1] = w[0];
+}
+
+// Everything emit_greedy() reads, from the heights: occupancy with halo, EX / EY / EZ, the X-plane masks and their
+// transposed equality rows, the non-empty rows of every plane.  Returns the OR of all face words.  sm.rows zeroed by the caller.
+__device__ __forceinline__ uint32_t masks_from_heights_g(mesh::SmemG& sm, const short* s_h, int Y0) {
+    using namespace mesh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PostG& P = sm.tile.post;
+    uint32_t ta[8], tb[8];                                            // to transpose: occupancy, EX | EY, EZ (four layers each)
+    uint32_t acc = 0, rx0 = 0, rx1 = 0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
-        slab4[tid + k * kThreads] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int k = 0; k < 4; ++k) {
+        const int z = k * kWarps + warp, x = lane;
+        const short* hp = s_h + (z + 1) * 34 + x + 1;
+        const int t = hp[0] - Y0;
+        const ColumnWords c = column_words(t), cz = column_words(hp[-34] - Y0);   // this column and its -z neighbour
+        uint32_t left = __shfl_up_sync(kFull, c.occ, 1), right = __shfl_down_sync(kFull, c.occ, 1);
+        if (x == 0) left = bits_le(hp[-1] - Y0);                      // the halo columns
+        if (x == 31) right = bits_le(hp[1] - Y0);
+        const uint32_t xm0 = c.occ & ~left, xm1 = c.occ & ~right;     // -X / +X visible, bit y: plane x, row z as it is
+        P.xmask[(0 * 32 + x) * kPad + z] = xm0;
+        P.xmask[(1 * 32 + x) * kPad + z] = xm1;
+        rx0 |= (uint32_t)(xm0 != 0u) << z;
+        rx1 |= (uint32_t)(xm1 != 0u) << z;
+        acc |= xm0 | xm1;
+        uint32_t l0 = __shfl_up_sync(kFull, c.p0, 1), l1 = __shfl_up_sync(kFull, c.p1, 1), l2 = __shfl_up_sync(kFull, c.p2, 1);
+        if (x == 0) l0 = l1 = l2 = 0u;
+        const uint32_t dx = (c.p0 ^ l0) | (c.p1 ^ l1) | (c.p2 ^ l2);
+        const uint32_t dy = ((c.p0 ^ (c.p0 << 1)) | (c.p1 ^ (c.p1 << 1)) | (c.p2 ^ (c.p2 << 1))) & ~1u;
+        const uint32_t dz = z > 0 ? (c.p0 ^ cz.p0) | (c.p1 ^ cz.p1) | (c.p2 ^ cz.p2) : 0u;
+        P.ht[x * kPad + z] = ~dy;                                     // X planes: u = y, v = z
+        P.vt[x * kPad + z] = ~dz;
+        ta[k] = c.occ;
+        ta[4 + k] = ~dx;
+        tb[k] = ~dy;
+        tb[4 + k] = ~dz;
+        // Y halo rows (y = -1, 32) of layer z, bit x
+        const uint32_t b_lo = __ballot_sync(kFull, t >= -1), b_hi = __ballot_sync(kFull, t >= 32);
+        if (lane == 0) { sm.occ[(z + 1) * 34] = b_lo; sm.occ[(z + 1) * 34 + 33] = b_hi; }
     }
+    transpose32xN(ta, lane);
+    transpose32xN(tb, lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                     // lane = y now
+        const int z = k * kWarps + warp, y = lane;
+        sm.occ[(z + 1) * 34 + y + 1] = ta[k];
+        sm.eq[0][z * kPad + y] = ta[4 + k];
+        sm.eq[1][z * kPad + y] = tb[k];
+        sm.eq[2][z * kPad + y] = tb[4 + k];
+    }
+    z_halo_from_heights(sm, s_h, Y0);
+    if (rx0) atomicOr(&sm.rows[0 * 32 + lane], rx0);
+    if (rx1) atomicOr(&sm.rows[1 * 32 + lane], rx1);
+    __syncthreads();                                                  // occupancy with halo published
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int z = k * kWarps + warp, y = lane;
+        const uint32_t* o = sm.occ + (z + 1) * 34 + (y + 1);
+        const uint32_t c = ta[k];
+        const uint32_t my = c & ~o[-1], py = c & ~o[+1], mz = c & ~o[-34], pz = c & ~o[+34];
+        acc |= my | py | mz | pz;
+        const uint32_t bz0 = __ballot_sync(kFull, mz != 0u), bz1 = __ballot_sync(kFull, pz != 0u);
+        if (lane == 0) { sm.rows[4 * 32 + z] = bz0; sm.rows[5 * 32 + z] = bz1; }
+        if (my) atomicOr(&sm.rows[2 * 32 + y], 1u << z);
+        if (py) atomicOr(&sm.rows[3 * 32 + y], 1u << z);
+    }
+    return acc;
 }
+
 template <class SM>
 __device__ __forceinline__ int load_footprint(SM& sm, const vxp_coord* __restrict__ coords, const ColumnScratch& cs, uint32_t chunk) {
     const int tid = threadIdx.x;
@@ -282,48 +346,45 @@ __device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemG& sm, const vxp_co
     prof.start(false);
     const int Y0 = load_footprint(sm, coords, cs, chunk);
     const short* s_h = sm.aux.heights;
-    __syncthreads();
-    halo_from_heights(sm.occ, sm.xh, s_h, Y0);
-    uint32_t v_or = 0, v_and = kFull, o_and = kFull;
-    mesh::IdPlanes ip;
-#pragma unroll
-    for (int s = 0; s < mesh::kSlabs; ++s) {
-        generate_slab(sm.tile.ring[s & 1], s_h, Y0, s);
-        __syncthreads();                              // slab s complete (and slab s-1 converted by everybody: its buffer is next)
-        mesh::convert_ring_slab(sm, s, v_or, v_and, o_and, ip);
-    }
-    const mesh::ChunkFlags fl = mesh::reduce_flags_g(sm, v_or, v_and, o_and);   // barriers: occupancy and halo published, ring dead
-    const bool with_eq = !fl.single_id;               // terrain ids are 1..4: a chunk with several ids always takes the plane path
-    if (with_eq) mesh::store_id_planes_g(sm, ip);
     if (tid < 192) sm.rows[tid] = 0u;
     __syncthreads();
-    const bool any = __syncthreads_or(mesh::build_masks_g(sm, with_eq, with_eq) != 0);
+    const bool any = __syncthreads_or(masks_from_heights_g(sm, s_h, Y0) != 0);
     if (!any) {
         if (tid == 0) out.meta[chunk] = vxp_chunk_meta{0u, 0u};
         return;
     }
-    mesh::emit_greedy(sm, chunk, with_eq, out, [s_h, Y0](int idx) -> uint32_t {
+    // terrain ids are 1..4: the equality rows always come from the id planes
+    mesh::emit_greedy(sm, chunk, true, out, [s_h, Y0](int idx) -> uint32_t {
         const int x = idx & 31, y = (idx >> 5) & 31, z = idx >> 10;
         return terrain_block(s_h[(z + 1) * 34 + x + 1], Y0 + y);
     }, prof);
 }
 __device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemC& sm, const vxp_coord* __restrict__ coords,
                                                    const ColumnScratch& cs, uint32_t chunk, const mesh::MeshOut& out) {
-    mesh::Prof prof;
+    using namespace mesh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Prof prof;
     prof.start(false);
     const int Y0 = load_footprint(sm, coords, cs, chunk);
     const short* s_h = sm.aux.heights;
     __syncthreads();
-    halo_from_heights(sm.occ, sm.xh, s_h, Y0);
-    uint32_t v_or = 0, o_and = kFull;
-#pragma unroll 1
-    for (int s = 0; s < mesh::kSlabs; ++s) {
-        generate_slab(sm.tile.ring[s & 1], s_h, Y0, s);
-        __syncthreads();
-        mesh::convert_ring_slab_c(sm, s, v_or, o_and);
+    // occupancy only: words over y per column, transposed to words over x; halo rows by ballot / transpose / as they are
+    uint32_t ta[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int z = k * kWarps + warp;
+        const int t = s_h[(z + 1) * 34 + lane + 1] - Y0;
+        ta[k] = bits_le(t);
+        const uint32_t b_lo = __ballot_sync(kFull, t >= -1), b_hi = __ballot_sync(kFull, t >= 32);
+        if (lane == 0) { sm.occ[(z + 1) * 34] = b_lo; sm.occ[(z + 1) * 34 + 33] = b_hi; }
     }
-    __syncthreads();                                  // occupancy and halo published, ring dead
-    mesh::culled_emit_c(sm, chunk, mesh::culled_count<false>(sm) + mesh::culled_count<true>(sm), out, [s_h, Y0](int idx) -> uint32_t {
+    transpose32xN(ta, lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sm.occ[(k * kWarps + warp + 1) * 34 + lane + 1] = ta[k];
+    z_halo_from_heights(sm, s_h, Y0);
+    if (tid < 64) sm.xh[tid >> 5][tid & 31] = bits_le(s_h[((tid & 31) + 1) * 34 + ((tid >> 5) ? 33 : 0)] - Y0);   // X halos: bit y per z
+    __syncthreads();                                  // occupancy and halo published
+    culled_emit_c(sm, chunk, culled_count<false>(sm) + culled_count<true>(sm), out, [s_h, Y0](int idx) -> uint32_t {
         const int x = idx & 31, y = (idx >> 5) & 31, z = idx >> 10;
         return terrain_block(s_h[(z + 1) * 34 + x + 1], Y0 + y);
     }, prof);
