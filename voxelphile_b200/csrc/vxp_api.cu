@@ -311,16 +311,17 @@ vxp_status column_scratch(vxp_ctx* ctx, uint32_t n, vxp::ColumnScratch* out) {
     if (n > ctx->columns_cap) {
         const size_t want = (size_t)n + n / 4;
         const size_t slots = vxp::column_table_slots((uint32_t)want);
-        const size_t b_keys = up(slots * 8), b_ids = up(slots * 4), b_slot = up(want * 8), b_coord = up(want * 8),
+        const size_t b_keys = up(slots * 8), b_ids = up(slots * 4), b_slot = up(want * 4), b_work = up(want * 16), b_coord = up(want * 8),
                      b_h = up(want * vxp::column_record_bytes()), b_cnt = 256;
         if (ctx->d_columns) VXP_CUDA(ctx, cudaFree(ctx->d_columns));
         ctx->d_columns = nullptr;
         ctx->columns_cap = 0;
-        VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_columns), b_keys + b_ids + b_slot + b_coord + b_h + b_cnt));
+        VXP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_columns), b_keys + b_ids + b_slot + b_work + b_coord + b_h + b_cnt));
         unsigned char* p = ctx->d_columns;
         ctx->columns.keys = reinterpret_cast<unsigned long long*>(p); p += b_keys;
         ctx->columns.id_of_slot = reinterpret_cast<uint32_t*>(p); p += b_ids;
         ctx->columns.slot_of_chunk = reinterpret_cast<uint32_t*>(p); p += b_slot;
+        ctx->columns.work = reinterpret_cast<uint4*>(p); p += b_work;
         ctx->columns.coord_of_id = reinterpret_cast<int2*>(p); p += b_coord;
         ctx->columns.heights = reinterpret_cast<short*>(p); p += b_h;
         ctx->columns.count = reinterpret_cast<uint32_t*>(p);

@@ -88,7 +88,12 @@ __global__ void __launch_bounds__(kThreads) pattern_fill_kernel(const vxp_coord*
 //                          finished here, the others go on a work list
 //   terrain_mesh_kernel    persistent CTAs draw work items from a ticket counter, generate the chunk slab by slab
 //                          into the ring of vxp_mesh.cuh and run its pipeline; voxels never reach HBM.
-constexpr int kColStride = 34 * 34 + 4;            // shorts per column record: footprint, hmin, hmax, 2 pad (8-byte multiple)
+constexpr int kColStride = 34 * 34 + 12;           // shorts per column record: footprint, hmin, hmax, kColBands band counts, 2 pad (8-byte multiple)
+constexpr int kColBands = 8;                       // band b = chunk layer (hmin >> 5) + b: how many of the footprint's columns end in it
+#ifndef VXP_HEAVY_MIN
+#define VXP_HEAVY_MIN 400
+#endif
+constexpr int kHeavyMin = VXP_HEAVY_MIN;           // a chunk with at least this many column tops goes to the front of the work list
 constexpr int kKeyEpochShift = 54;                 // key = epoch << 54 | (cx & 0x7FFFFFF) << 27 | (cz & 0x7FFFFFF)
 
 __device__ __forceinline__ unsigned long long column_key(int cx, int cz, uint32_t epoch) {
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) column_insert_kernel(const vxp_coord
 }
 __global__ void __launch_bounds__(kThreads) column_heights_kernel(ColumnScratch cs, uint64_t seed) {
     __shared__ TerrainLattice s_lat;
-    __shared__ int s_red[2 * kWarps];
+    __shared__ int s_red[2 * kWarps], s_band[kColBands];
     mesh::griddep_launch_dependents();
     mesh::griddep_wait();                              // the columns of this call have been inserted
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,13 +154,22 @@ __global__ void __launch_bounds__(kThreads) column_heights_kernel(ColumnScratch 
         hmin = __reduce_min_sync(kFull, hmin);
         hmax = __reduce_max_sync(kFull, hmax);
         if (lane == 0) { s_red[warp] = hmin; s_red[kWarps + warp] = hmax; }
+        if (tid < kColBands) s_band[tid] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kWarps + w]); }
+        // how many column tops fall into each 32-layer band from hmin's up: what a chunk of this column will cost
+        for (int i = tid; i < 34 * 34; i += kThreads) {
+            const int zz = i / 34 - 1, xx = i % 34 - 1;
+            if ((zz < 0 || zz > 31) && (xx < 0 || xx > 31)) continue;
+            atomicAdd(&s_band[min(((int)dst[i] >> 5) - (hmin >> 5), kColBands - 1)], 1);
+        }
         __syncthreads();
         if (tid == 0) {
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kWarps + w]); }
             dst[34 * 34] = (short)hmin;
             dst[34 * 34 + 1] = (short)hmax;
         }
+        if (tid < kColBands) dst[34 * 34 + 2 + tid] = (short)s_band[tid];
         __syncthreads();
     }
 }
@@ -168,19 +182,34 @@ __global__ void __launch_bounds__(kThreads) column_classify_kernel(const vxp_coo
     mesh::griddep_wait();                              // heights written
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool surface = false;
+    bool surface = false, heavy = false;
+    uint32_t id = 0;
+    int cy = 0;
     if (i < n) {
-        const short* col = cs.heights + (size_t)cs.id_of_slot[cs.slot_of_chunk[i]] * kColStride;
-        const int hmin = col[34 * 34], hmax = col[34 * 34 + 1], Y0 = 32 * coords[i].y;
+        id = cs.id_of_slot[cs.slot_of_chunk[i]];
+        cy = coords[i].y;
+        const short* col = cs.heights + (size_t)id * kColStride;
+        const int hmin = col[34 * 34], hmax = col[34 * 34 + 1], Y0 = 32 * cy;
         surface = !(Y0 > hmax || Y0 + 32 <= hmin);
         if (!surface) meta[i] = vxp_chunk_meta{0u, 0u};
+        else heavy = col[34 * 34 + 2 + min(max(cy - (hmin >> 5), 0), kColBands - 1)] >= kHeavyMin;
     }
-    const uint32_t m = __ballot_sync(kFull, surface);          // one list reservation per warp
-    if (m == 0) return;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(cs.count + 1, (uint32_t)__popc(m));
-    base = __shfl_sync(kFull, base, 0);
-    if (surface) cs.slot_of_chunk[n + base + __popc(m & ((1u << lane) - 1u))] = i;   // work list lives behind slot_of_chunk
+    // The work list is filled from both ends, one reservation per warp and end: chunks that hold many column tops (the
+    // expensive ones: their cost goes with their quads) from the front, the others from the back.  The mesh kernel draws
+    // from the front first, so the long items start early and the short ones fill the tail.
+    const uint32_t mh = __ballot_sync(kFull, surface && heavy), ml = __ballot_sync(kFull, surface && !heavy);
+    if ((mh | ml) == 0) return;
+    uint32_t bh = 0, bl = 0;
+    if (lane == 0) {
+        if (mh) bh = atomicAdd(cs.count + 1, (uint32_t)__popc(mh));
+        if (ml) bl = atomicAdd(cs.count + 6, (uint32_t)__popc(ml));
+    }
+    bh = __shfl_sync(kFull, bh, 0);
+    bl = __shfl_sync(kFull, bl, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    const uint4 entry = make_uint4(i, id, (uint32_t)cy, 0u);   // all the mesh kernel needs to start on the chunk
+    if (surface && heavy) cs.work[bh + __popc(mh & below)] = entry;
+    if (surface && !heavy) cs.work[n - 1u - (bl + __popc(ml & below))] = entry;
 }
 
 // Terrain fill of a large batch: the chunks of a column (cx,cz) share its heights (column_insert_kernel /
@@ -331,20 +360,20 @@ __device__ __forceinline__ uint32_t masks_from_heights_g(mesh::SmemG& sm, const 
 }
 
 template <class SM>
-__device__ __forceinline__ int load_footprint(SM& sm, const vxp_coord* __restrict__ coords, const ColumnScratch& cs, uint32_t chunk) {
+__device__ __forceinline__ int load_footprint(SM& sm, const ColumnScratch& cs, const uint4& item) {   // item: {chunk, column id, chunk y}
     const int tid = threadIdx.x;
-    const short* col = cs.heights + (size_t)cs.id_of_slot[cs.slot_of_chunk[chunk]] * kColStride;
+    const short* col = cs.heights + (size_t)item.y * kColStride;
     for (int i = tid; i < 34 * 34 / 2; i += kThreads)     // 2312 bytes, 4 at a time
         reinterpret_cast<uint32_t*>(sm.aux.heights)[i] = __ldg(reinterpret_cast<const uint32_t*>(col) + i);
-    return 32 * coords[chunk].y;
+    return 32 * (int)item.z;
 }
 
-__device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemG& sm, const vxp_coord* __restrict__ coords,
-                                                   const ColumnScratch& cs, uint32_t chunk, const mesh::MeshOut& out) {
+__device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemG& sm, const ColumnScratch& cs, const uint4& item, const mesh::MeshOut& out) {
     const int tid = threadIdx.x;
+    const uint32_t chunk = item.x;
     mesh::Prof prof;
     prof.start(false);
-    const int Y0 = load_footprint(sm, coords, cs, chunk);
+    const int Y0 = load_footprint(sm, cs, item);
     const short* s_h = sm.aux.heights;
     if (tid < 192) sm.rows[tid] = 0u;
     __syncthreads();
@@ -359,13 +388,13 @@ __device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemG& sm, const vxp_co
         return terrain_block(s_h[(z + 1) * 34 + x + 1], Y0 + y);
     }, prof);
 }
-__device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemC& sm, const vxp_coord* __restrict__ coords,
-                                                   const ColumnScratch& cs, uint32_t chunk, const mesh::MeshOut& out) {
+__device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemC& sm, const ColumnScratch& cs, const uint4& item, const mesh::MeshOut& out) {
     using namespace mesh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t chunk = item.x;
     Prof prof;
     prof.start(false);
-    const int Y0 = load_footprint(sm, coords, cs, chunk);
+    const int Y0 = load_footprint(sm, cs, item);
     const short* s_h = sm.aux.heights;
     __syncthreads();
     // occupancy only: words over y per column, transposed to words over x; halo rows by ballot / transpose / as they are
@@ -390,7 +419,7 @@ __device__ __forceinline__ void terrain_mesh_chunk(mesh::SmemC& sm, const vxp_co
     }, prof);
 }
 
-// cs.count: [0] columns, [1] work items, [2] ticket, [3] CTAs done, [4..5] quads reserved (64 bit): all zero between calls
+// cs.count: [0] columns, [1] heavy work items, [2] ticket, [3] CTAs done, [4..5] quads reserved (64 bit), [6] light work items: all zero between calls
 template <bool kGreedy>
 __global__ void __launch_bounds__(kThreads, kGreedy ? mesh::kGreedyCtas : mesh::kCulledCtas)
 terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, ColumnScratch cs, mesh::MeshOut out,
@@ -398,20 +427,43 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, ColumnScra
     using SM = std::conditional_t<kGreedy, mesh::SmemG, mesh::SmemC>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
-    __shared__ uint32_t s_item[2];
+    __shared__ uint4 s_item[2];
     mesh::griddep_wait();                             // work list complete
-    const uint32_t nwork = cs.count[1];
+    const uint32_t nheavy = cs.count[1], nwork = nheavy + cs.count[6];
+    const uint4 none = make_uint4(~0u, 0u, 0u, 0u);
+    auto entry_of = [&](uint32_t t) { return cs.work[t < nheavy ? t : n - 1u - (t - nheavy)]; };   // heavy items first (see column_classify_kernel)
+    // Work items are drawn from a ticket counter (chunk costs vary widely), two ahead: while item k is meshed, thread 0
+    // has the ticket of k+1 in hand, fetches that item's entry and draws the ticket of k+2 - both round trips hide
+    // behind the chunk, and an item starts with everything it needs to request its heights.
+    uint32_t t_next = 0;
     if (threadIdx.x == 0) {
         if constexpr (kGreedy) { sm.ones = kFull; sm.zero = 0u; }
-        s_item[0] = atomicAdd(cs.count + 2, 1u);
+        const uint32_t t0 = atomicAdd(cs.count + 2, 1u);
+        t_next = atomicAdd(cs.count + 2, 1u);
+        s_item[0] = t0 < nwork ? entry_of(t0) : none;
     }
     __syncthreads();
-    for (uint32_t it = 0;; ++it) {                    // work items are drawn from a ticket counter: chunk costs vary widely
-        const uint32_t item = s_item[it & 1];
-        if (item >= nwork) break;
-        if (threadIdx.x == 0) s_item[(it + 1) & 1] = atomicAdd(cs.count + 2, 1u);   // its latency hides behind this chunk
-        terrain_mesh_chunk(sm, coords, cs, cs.slot_of_chunk[n + item], out);
-        __syncthreads();                              // shared memory is free again, the next ticket is visible
+    for (uint32_t it = 0;; ++it) {
+        const uint4 item = s_item[it & 1];
+        if (item.x == ~0u) break;
+        uint4 upcoming = none;
+        uint32_t t_after = 0;
+        if (threadIdx.x == 0) {
+            if (t_next < nwork) upcoming = entry_of(t_next);
+            t_after = atomicAdd(cs.count + 2, 1u);
+        }
+#ifdef VXP_PROFILE
+        if (threadIdx.x == 0 && item.x < mesh::kProfCtas) mesh::g_prof_time[item.x][0] = mesh::prof_now();
+#endif
+        terrain_mesh_chunk(sm, cs, item, out);
+#ifdef VXP_PROFILE
+        if (threadIdx.x == 0 && item.x < mesh::kProfCtas) mesh::g_prof_time[item.x][1] = mesh::prof_now();
+#endif
+        if (threadIdx.x == 0) {
+            s_item[(it + 1) & 1] = upcoming;
+            t_next = t_after;
+        }
+        __syncthreads();                              // shared memory is free again, the next item is visible
     }
     if (threadIdx.x == 0) {
         __threadfence();                              // this CTA's reservations are ordered before its check-out
@@ -422,6 +474,7 @@ terrain_mesh_kernel(const vxp_coord* __restrict__ coords, uint32_t n, ColumnScra
             cs.count[1] = 0u;
             cs.count[2] = 0u;
             cs.count[3] = 0u;
+            cs.count[6] = 0u;
         }
     }
 }

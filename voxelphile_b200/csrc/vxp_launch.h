@@ -19,8 +19,8 @@ size_t boundary_plane_bytes(uint32_t n);
 
 // Context-owned scratch of the fused terrain+mesh path: the chunks of a batch that share a column (cx,cz)
 // share one height footprint.  Sized for a batch of n chunks: keys / id_of_slot have column_table_slots(n)
-// entries (a power of two, mask = slots - 1), slot_of_chunk has 2n (the second half is the work list of
-// chunks that cross the surface), coord_of_id n, heights n records of column_record_bytes(), count
+// entries (a power of two, mask = slots - 1), slot_of_chunk has n, work (the list of the chunks that cross the
+// surface, with what the mesh kernel needs to start on one) up to n, coord_of_id n, heights n records of column_record_bytes(), count
 // kColumnCounterWords words (columns, work items, ticket, CTAs done, 64-bit quad counter; 8-byte aligned).
 // keys and count must be zero-filled when allocated.  keys are stamped with `epoch` (in [1, 1023], advanced by
 // the owner per call; the owner re-zeroes keys when it wraps), so no call starts with a memset; the fused mesh
@@ -30,6 +30,7 @@ struct ColumnScratch {
     unsigned long long* keys;
     uint32_t* id_of_slot;
     uint32_t* slot_of_chunk;
+    uint4* work;                 // work list of the fused mesh kernel: {chunk, column id, chunk y, 0}
     int2* coord_of_id;
     short* heights;
     uint32_t* count;
