@@ -24,7 +24,7 @@ constexpr int kSlabs = 4;
 // ---- optional per-phase cycle accounting (profiling build only: -DVXP_PROFILE, libvxp_prof.so)
 #ifdef VXP_PROFILE
 constexpr int kProfSlots = 16;
-constexpr int kProfCtas = 8192;
+constexpr int kProfCtas = 65536;
 __device__ unsigned long long g_prof[kProfCtas][kProfSlots];
 __device__ unsigned int g_prof_warp[kProfCtas][8];   // per-warp cycles of the greedy sweep
 __device__ unsigned long long g_prof_time[kProfCtas][2];   // %globaltimer (ns) at CTA start / end
