@@ -126,9 +126,12 @@ __global__ void __launch_bounds__(kThreads) column_insert_kernel(const vxp_coord
     }
     cs.slot_of_chunk[i] = slot;
 }
-__global__ void __launch_bounds__(kThreads) column_heights_kernel(ColumnScratch cs, uint64_t seed) {
+// 608 threads: the 1156 heights of a footprint are two per thread (a height is a chain of ~180 dependent instructions, and
+// with few columns - an eighth of a world per GPU - the kernel is one wave of that latency)
+constexpr int kHeightThreads = 608, kHeightWarps = kHeightThreads / 32;
+__global__ void __launch_bounds__(kHeightThreads) column_heights_kernel(ColumnScratch cs, uint64_t seed) {
     __shared__ TerrainLattice s_lat;
-    __shared__ int s_red[2 * kWarps], s_band[kColBands];
+    __shared__ int s_red[2 * kHeightWarps], s_band[kColBands];
     mesh::griddep_launch_dependents();
     mesh::griddep_wait();                              // the columns of this call have been inserted
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,30 +143,32 @@ __global__ void __launch_bounds__(kThreads) column_heights_kernel(ColumnScratch 
         __syncthreads();
         short* dst = cs.heights + (size_t)col * kColStride;
         int hmin = INT_MAX, hmax = INT_MIN;
-        for (int i = tid; i < 34 * 34; i += kThreads) {
+        int h[2];
+        bool real[2];                                  // corners of the footprint are nobody's neighbour: not computed
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = tid + k * kHeightThreads;
             const int zz = i / 34 - 1, xx = i % 34 - 1;
-            const bool corner = (zz < 0 || zz > 31) && (xx < 0 || xx > 31);
-            int h = 0;
-            if (!corner) {
-                h = terrain_height_lattice(s_lat, 32 * c.x + xx, 32 * c.y + zz);
-                hmin = min(hmin, h);
-                hmax = max(hmax, h);
+            real[k] = i < 34 * 34 && !((zz < 0 || zz > 31) && (xx < 0 || xx > 31));
+            h[k] = 0;
+            if (real[k]) {
+                h[k] = terrain_height_lattice(s_lat, 32 * c.x + xx, 32 * c.y + zz);
+                hmin = min(hmin, h[k]);
+                hmax = max(hmax, h[k]);
             }
-            dst[i] = (short)h;
+            if (i < 34 * 34) dst[i] = (short)h[k];
         }
         hmin = __reduce_min_sync(kFull, hmin);
         hmax = __reduce_max_sync(kFull, hmax);
-        if (lane == 0) { s_red[warp] = hmin; s_red[kWarps + warp] = hmax; }
+        if (lane == 0) { s_red[warp] = hmin; s_red[kHeightWarps + warp] = hmax; }
         if (tid < kColBands) s_band[tid] = 0;
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kWarps + w]); }
+        for (int w = 0; w < kHeightWarps; ++w) { hmin = min(hmin, s_red[w]); hmax = max(hmax, s_red[kHeightWarps + w]); }
         // how many column tops fall into each 32-layer band from hmin's up: what a chunk of this column will cost
-        for (int i = tid; i < 34 * 34; i += kThreads) {
-            const int zz = i / 34 - 1, xx = i % 34 - 1;
-            if ((zz < 0 || zz > 31) && (xx < 0 || xx > 31)) continue;
-            atomicAdd(&s_band[min(((int)dst[i] >> 5) - (hmin >> 5), kColBands - 1)], 1);
-        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (real[k]) atomicAdd(&s_band[min((h[k] >> 5) - (hmin >> 5), kColBands - 1)], 1);
         __syncthreads();
         if (tid == 0) {
             dst[34 * 34] = (short)hmin;
@@ -497,10 +502,11 @@ cudaError_t configure_device() {
 // A launch that may become resident while its predecessor on the stream is still running (programmatic dependent
 // launch); the kernel waits for the predecessor's results itself (griddepcontrol.wait).
 template <class... Params, class... Args>
-static cudaError_t launch_dependent(void (*kernel)(Params...), uint32_t grid, size_t smem, cudaStream_t stream, Args... args) {
+static cudaError_t launch_dependent_threads(void (*kernel)(Params...), uint32_t grid, uint32_t threads, size_t smem, cudaStream_t stream,
+                                            Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -509,6 +515,10 @@ static cudaError_t launch_dependent(void (*kernel)(Params...), uint32_t grid, si
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+template <class... Params, class... Args>
+static cudaError_t launch_dependent(void (*kernel)(Params...), uint32_t grid, size_t smem, cudaStream_t stream, Args... args) {
+    return launch_dependent_threads(kernel, grid, (uint32_t)kThreads, smem, stream, args...);
 }
 
 static int sm_count() {
@@ -532,7 +542,7 @@ static cudaError_t launch_columns(const vxp_coord* d_coords, uint32_t n, uint64_
     if (e != cudaSuccess) return e;
     const uint32_t sms = (uint32_t)sm_count();
     const uint32_t hgrid = n < 4 * sms ? n : 4 * sms;
-    return launch_dependent(column_heights_kernel, hgrid, 0, stream, cs, seed);
+    return launch_dependent_threads(column_heights_kernel, hgrid, (uint32_t)kHeightThreads, 0, stream, cs, seed);
 }
 
 cudaError_t launch_terrain_fill_columns(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
