@@ -807,6 +807,28 @@ def test_greedy_staging_fallbacks(mesher):
     check_against_oracle(host, vox, None, 1)
 
 
+def test_greedy_log_overflow_in_halves(mesher):
+    """Chunks whose sweep log does not fit in one piece but does in two halves of the planes (between 1985 and ~2900
+    non-empty plane rows): scattered single voxels at 1.2 % .. 2 % density, one and several ids, with and without a
+    neighbour; denser ones take the stepped sweep (covered above)."""
+    rng = np.random.default_rng(77)
+    dens = (0.012, 0.014, 0.016, 0.018, 0.020, 0.024)
+    vox = np.zeros((2 * len(dens) + 1, 32768), dtype=np.uint16)
+    for k, p in enumerate(dens):
+        hit = rng.random(32768) < p
+        vox[2 * k][hit] = 3
+        vox[2 * k + 1] = np.where(rng.random(32768) < p, rng.integers(1, 6, 32768), 0)
+    vox[-1] = np.where(rng.random(32768) < 0.3, 2, 0)                 # something to look at across +x
+    nbr = np.full((vox.shape[0], 6), -1, dtype=np.int32)
+    nbr[:-1, 1] = vox.shape[0] - 1
+    for mode in (1,):
+        host = gpu_mesh(mesher, vox, nbr, mode)
+        check_against_oracle(host, vox, nbr, mode)
+    # the rows of such a chunk: every voxel is alone, so it has one row in six planes
+    rows = [6 * int((vox[i] != 0).sum()) for i in range(len(vox) - 1)]
+    assert min(rows) < 2944 and max(rows) > 1984
+
+
 # --------------------------------------------------------------------------- SPEC §11: level of detail
 def test_downsample_and_mesh_lod(mesher):
     """vxp_downsample_chunks against the numpy restatement (random chunks, missing children, terrain), and the
