@@ -53,38 +53,46 @@ struct __align__(128) SmemG {
         unsigned char ring[2][kSlabBytes];
         PostG post;
     } tile;
+    // eq .. first_run are dead while the chunk streams (the id planes are in registers until it has been read): the
+    // third ring buffer lies over them
     uint32_t eq[3][kPlaneWords];   // [b][z*33+y]: id plane b while streaming; afterwards EX / EY / EZ (same layout as v4's ex / ey / ez)
-    uint32_t occ[34 * 34];
     Aux aux;                       // second streaming pass: the last layer of the previous slab / fused path: heights
-    uint32_t xh[2][32];
-    uint32_t actz[32];
-    uint32_t scratch[kWarps + 1];
     uint32_t seg[192];
     uint32_t rows[192];
     uint32_t first_run[192];
+    uint32_t occ[34 * 34];
+    uint32_t xh[2][32];
+    uint32_t actz[32];
+    uint32_t scratch[kWarps + 1];
     uint32_t cursor;
     uint32_t counted;
     uint32_t ones;                 // 0xFFFFFFFF: stand-in equality row for single-id chunks
     uint32_t zero;                 // 0: stand-in "neighbour" row of the stored X masks
     uint32_t ref;                  // voxels 0 and 1 of the chunk
     unsigned long long first;
-    unsigned long long mbar[2];
+    unsigned long long mbar[3];
 };
 static_assert(sizeof(PostG) <= 2 * kSlabBytes, "post layout overflows the ring");
+static_assert(offsetof(SmemG, eq) == 2 * kSlabBytes && offsetof(SmemG, occ) >= 3 * kSlabBytes, "the third ring buffer overlays eq .. first_run");
+#ifndef VXP_RING
+#define VXP_RING 3
+#endif
+constexpr int kRingG = VXP_RING;   // ring buffers of the greedy kernel's first pass (2: the tile only)
 // per CTA: the struct + 128 bytes of static shared memory (fused kernel) + 1 KiB the driver reserves; 227 KiB per SM
 static_assert(kGreedyCtas * (sizeof(SmemG) + 128 + 1024) <= 227 * 1024, "shared memory of the greedy kernels exceeds the CTAs-per-SM target");
 
 // ------------------------------------------------------------------ streaming
-__device__ __forceinline__ void issue_ring_slab(SmemG& sm, const uint16_t* gvox, int s) {
-    mbar_expect_tx(&sm.mbar[s & 1], kSlabBytes);
-    tma_load_1d(sm.tile.ring[s & 1], reinterpret_cast<const unsigned char*>(gvox) + (size_t)s * kSlabBytes, kSlabBytes,
-                &sm.mbar[s & 1]);
+// ring buffer b: 0, 1 = the tile, 2 = over eq .. first_run
+__device__ __forceinline__ unsigned char* ring_buffer(SmemG& sm, int b) { return reinterpret_cast<unsigned char*>(&sm) + b * kSlabBytes; }
+__device__ __forceinline__ void issue_ring_slab(SmemG& sm, const uint16_t* gvox, int s, int b) {
+    mbar_expect_tx(&sm.mbar[b], kSlabBytes);
+    tma_load_1d(ring_buffer(sm, b), reinterpret_cast<const unsigned char*>(gvox) + (size_t)s * kSlabBytes, kSlabBytes, &sm.mbar[b]);
 }
 
-// Slab s (in ring buffer s & 1) -> occupancy bytes and id-plane bytes, straight into shared memory.
-__device__ __forceinline__ void convert_ring_slab(SmemG& sm, int s, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and, IdPlanes& ip) {
+// Slab s (in ring buffer b) -> occupancy bytes and id-plane bytes, straight into shared memory.
+__device__ __forceinline__ void convert_ring_slab(SmemG& sm, int s, int b, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and, IdPlanes& ip) {
     const int tid = threadIdx.x;
-    const uint4* slab = reinterpret_cast<const uint4*>(sm.tile.ring[s & 1]);
+    const uint4* slab = reinterpret_cast<const uint4*>(ring_buffer(sm, b));
     unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
     uint4 q[4];
     uint32_t slab_or = 0, slab_and = kFull;
@@ -162,18 +170,20 @@ __device__ __forceinline__ ChunkFlags reduce_flags_g(SmemG& sm, uint32_t v_or, u
 // rows that carry a visible face from the voxels themselves (slab by slab; the layer below a
 // slab's first one comes from sm.carry).  `phase` = number of completed phases of each ring barrier so far (2).
 __device__ __forceinline__ void equality_second_pass(SmemG& sm, const uint16_t* gvox) {
+    // completed phases of the two barriers after the first pass: ring of 2: 2 and 2; ring of 3: 2 (slabs 0, 3) and 1
+    constexpr uint32_t kDone0 = 2u, kDone1 = kRingG == 3 ? 1u : 2u;
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = lane & 3;
     const uint32_t selA = (p & 1) ? 0x3715u : 0x6240u;   // 4x4 byte transpose across the 4 lanes of a row
     const uint32_t selB = (p & 2) ? 0x3276u : 0x5410u;
     if (tid == 0) {
-        issue_ring_slab(sm, gvox, 0);
-        issue_ring_slab(sm, gvox, 1);
+        issue_ring_slab(sm, gvox, 0, 0);
+        issue_ring_slab(sm, gvox, 1, 1);
     }
 #pragma unroll 1
     for (int s = 0; s < kSlabs; ++s) {
-        mbar_wait(&sm.mbar[s & 1], (uint32_t)(s >> 1) & 1u);    // phases 2, 3 of each barrier: parities 0, 1 again
-        const uint4* slab = reinterpret_cast<const uint4*>(sm.tile.ring[s & 1]);
+        mbar_wait(&sm.mbar[s & 1], (((s & 1) ? kDone1 : kDone0) + (uint32_t)(s >> 1)) & 1u);
+        const uint4* slab = reinterpret_cast<const uint4*>(ring_buffer(sm, s & 1));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int idx = tid + k * kThreads;                  // within the slab
@@ -198,7 +208,7 @@ __device__ __forceinline__ void equality_second_pass(SmemG& sm, const uint16_t* 
         if (s + 1 < kSlabs) {
             if (tid < 128) sm.aux.carry[tid] = slab[7 * 128 + tid];  // layer 8s+7 for the first layer of slab s+1
             __syncthreads();
-            if (tid == 0 && s + 2 < kSlabs) issue_ring_slab(sm, gvox, s + 2);
+            if (tid == 0 && s + 2 < kSlabs) issue_ring_slab(sm, gvox, s + 2, s & 1);
         }
     }
 }
@@ -668,8 +678,8 @@ __device__ __forceinline__ void mesh_chunk_g(SmemG& sm, const uint16_t* __restri
     Prof prof;
     prof.start(tid == 0);
     if (tid == 0) {
-        issue_ring_slab(sm, gvox, 0);
-        issue_ring_slab(sm, gvox, 1);
+#pragma unroll
+        for (int s = 0; s < kRingG; ++s) issue_ring_slab(sm, gvox, s, s);
     }
     const int nb = (nbr6 && tid < 192) ? __ldg(nbr6 + 6 * (size_t)chunk + (tid >> 5)) : -1;
     HaloRows rows;
@@ -679,11 +689,11 @@ __device__ __forceinline__ void mesh_chunk_g(SmemG& sm, const uint16_t* __restri
     IdPlanes ip;
 #pragma unroll
     for (int s = 0; s < kSlabs; ++s) {
-        mbar_wait(&sm.mbar[s & 1], (uint32_t)(s >> 1) & 1u);
-        convert_ring_slab(sm, s, v_or, v_and, o_and, ip);
-        if (s + 2 < kSlabs) {
+        mbar_wait(&sm.mbar[s % kRingG], (uint32_t)(s / kRingG) & 1u);
+        convert_ring_slab(sm, s, s % kRingG, v_or, v_and, o_and, ip);
+        if (s + kRingG < kSlabs) {
             __syncthreads();                            // the buffer has been read by everybody
-            if (tid == 0) issue_ring_slab(sm, gvox, s + 2);
+            if (tid == 0) issue_ring_slab(sm, gvox, s + kRingG, s % kRingG);
         }
     }
     prof.mark(0);
@@ -746,6 +756,7 @@ mesh_kernel_g(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
         sm.counted = 0u;
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
+        mbar_init(&sm.mbar[2], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -1007,6 +1018,7 @@ mesh_kernel_c(const uint16_t* __restrict__ voxels, const int32_t* __restrict__ n
         sm.counted = 0u;
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
+        mbar_init(&sm.mbar[2], 1);
         fence_mbar_init();
     }
     __syncthreads();
