@@ -89,20 +89,27 @@ __device__ __forceinline__ void issue_ring_slab(SmemG& sm, const uint16_t* gvox,
     tma_load_1d(ring_buffer(sm, b), reinterpret_cast<const unsigned char*>(gvox) + (size_t)s * kSlabBytes, kSlabBytes, &sm.mbar[b]);
 }
 
-// Slab s (in ring buffer b) -> occupancy bytes and id-plane bytes, straight into shared memory.
+// Slab s (in ring buffer b) -> occupancy words and id-plane words.  A thread converts one 64-byte row of the slab
+// (32 voxels -> one word of each kind, so one 4-byte store instead of four byte stores); a warp takes 8 values of y in
+// 4 layers, the shape that is most often one value in a terrain world (air above, rock below).  The four 16-byte pieces
+// of a row are read in an order rotated by lane / 2, which makes a quarter-warp touch every bank once, and the
+// finished words are rotated back.
+__device__ __forceinline__ int convert_row_z(int s) { return 8 * s + 4 * ((int)threadIdx.x >> 7) + (((int)threadIdx.x >> 3) & 3); }
+__device__ __forceinline__ int convert_row_y() { return 8 * (((int)threadIdx.x >> 5) & 3) + ((int)threadIdx.x & 7); }
 __device__ __forceinline__ void convert_ring_slab(SmemG& sm, int s, int b, uint32_t& v_or, uint32_t& v_and, uint32_t& o_and, IdPlanes& ip) {
-    const int tid = threadIdx.x;
-    const uint4* slab = reinterpret_cast<const uint4*>(ring_buffer(sm, b));
-    unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
-    uint4 q[4];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int j = (lane >> 1) & 3;
+    const int z = convert_row_z(s), y = convert_row_y();
+    const uint4* row = reinterpret_cast<const uint4*>(ring_buffer(sm, b)) + ((z & 7) * 32 + y) * 4;
+    uint4 q[4];                                                // q[k] = piece (k + j) & 3 of the row
     uint32_t slab_or = 0, slab_and = kFull;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        q[k] = slab[tid + k * kThreads];
+        q[k] = row[(k + j) & 3];
         slab_or |= q[k].x | q[k].y | q[k].z | q[k].w;
         slab_and &= q[k].x & q[k].y & q[k].z & q[k].w;
     }
-    if (s == 0 && tid == 0) sm.ref = q[0].x;
+    if (s == 0 && tid == 0) sm.ref = q[0].x;                   // thread 0 reads its pieces in order
     v_or |= slab_or;
     v_and &= slab_and;
     const uint32_t id = slab_or & 0xFFFFu;
@@ -115,44 +122,32 @@ __device__ __forceinline__ void convert_ring_slab(SmemG& sm, int s, int b, uint3
         p0 = (id & 1u) ? kFull : 0u;
         p1 = (id & 2u) ? kFull : 0u;
         p2 = (id & 4u) ? kFull : 0u;
-        o_and &= ob & 0xFFu;
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t bits = nz8(q[k]);
-            o_and &= bits;
-            ob |= bits << (8 * k);
-        }
+        for (int k = 0; k < 4; ++k) ob |= nz8(q[k]) << (8 * k);
         id_plane_bytes<0>(q[0], p0, p1, p2);
         id_plane_bytes<1>(q[1], p0, p1, p2);
         id_plane_bytes<2>(q[2], p0, p1, p2);
         id_plane_bytes<3>(q[3], p0, p1, p2);
+        const uint32_t rot = 8u * (uint32_t)j;                 // byte k holds piece (k + j) & 3: rotate it there
+        ob = __funnelshift_l(ob, ob, rot);
+        p0 = __funnelshift_l(p0, p0, rot);
+        p1 = __funnelshift_l(p1, p1, rot);
+        p2 = __funnelshift_l(p2, p2, rot);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int idx = tid + k * kThreads;
-        const int row = s * 256 + (idx >> 2), p = idx & 3;      // row = z*32 + y
-        const int z = row >> 5, y = row & 31;
-        occ_bytes[((z + 1) * 34 + y + 1) * 4 + p] = (unsigned char)(ob >> (8 * k));
-    }
+    o_and &= ob;
+    sm.occ[(z + 1) * 34 + y + 1] = ob;
 #pragma unroll
     for (int t = 0; t < kSlabs; ++t)                        // s is an unrolled loop counter of the caller: ip stays in registers
         if (t == s) { ip.w[0][t] = p0; ip.w[1][t] = p1; ip.w[2][t] = p2; }
 }
 // The id planes of a chunk that will use them (several ids, all small): registers -> sm.eq[b][z*33+y], bit x.
 __device__ __forceinline__ void store_id_planes_g(SmemG& sm, const IdPlanes& ip) {
-    const int tid = threadIdx.x;
-    unsigned char* base = reinterpret_cast<unsigned char*>(sm.eq);
 #pragma unroll
     for (int s = 0; s < kSlabs; ++s) {
+        const int word = convert_row_z(s) * kPad + convert_row_y();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int idx = tid + k * kThreads;
-            const int row = s * 256 + (idx >> 2), p = idx & 3;
-            const int word = (row >> 5) * kPad + (row & 31);
-#pragma unroll
-            for (int b = 0; b < kIdPlanes; ++b) base[(b * kPlaneWords + word) * 4 + p] = (unsigned char)(ip.w[b][s] >> (8 * k));
-        }
+        for (int b = 0; b < kIdPlanes; ++b) sm.eq[b][word] = ip.w[b][s];
     }
 }
 
@@ -160,7 +155,7 @@ __device__ __forceinline__ ChunkFlags reduce_flags_g(SmemG& sm, uint32_t v_or, u
     ChunkFlags f;
     f.any_solid = __syncthreads_or(v_or != 0u);                // barrier: occupancy, planes and sm.ref published
     const uint32_t ref = sm.ref;
-    f.all_solid = __syncthreads_and((o_and & 0xFFu) == 0xFFu);
+    f.all_solid = __syncthreads_and(o_and == kFull);
     f.single_id = __syncthreads_and(v_or == ref && v_and == ref && (ref & 0xFFFFu) == (ref >> 16));
     f.small_ids = __syncthreads_and(((v_or | (v_or >> 16)) & 0xFFFFu) < (1u << kIdPlanes));
     return f;

@@ -118,7 +118,7 @@ struct ChunkFlags {
 // out of the tile in a pass of their own 4.5 k; during the conversion 1.5 k.
 constexpr int kIdPlanes = 3;
 struct IdPlanes {
-    uint32_t w[kIdPlanes][kSlabs];   // w[b][s]: byte k = bit b of the 8 voxels of this thread's k-th piece of slab s
+    uint32_t w[kIdPlanes][kSlabs];   // w[b][s]: bit x = bit b of voxel x of this thread's row of slab s (convert_row_z / convert_row_y)
 };
 // The low kIdPlanes bits of 8 consecutive u16, one plane byte each (bit j of byte b = bit b of element j), placed
 // in byte k of p0 / p1 / p2.  Three steps: the low bytes of the 8 elements are packed into two words (2 PRMT) and
