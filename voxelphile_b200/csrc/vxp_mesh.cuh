@@ -819,14 +819,16 @@ __device__ __forceinline__ void issue_ring_slab_c(SmemC& sm, const uint16_t* gvo
 }
 // Slab s -> occupancy bytes; v_or / o_and accumulate "any voxel" / "all voxels" per thread.
 __device__ __forceinline__ void convert_ring_slab_c(SmemC& sm, int s, uint32_t& v_or, uint32_t& o_and) {
-    const int tid = threadIdx.x;
-    const uint4* slab = reinterpret_cast<const uint4*>(sm.tile.ring[s & 1]);
-    unsigned char* occ_bytes = reinterpret_cast<unsigned char*>(sm.occ);
+    // one 64-byte row per thread, read and stored as in convert_ring_slab (greedy)
+    const int lane = threadIdx.x & 31;
+    const int j = (lane >> 1) & 3;
+    const int z = convert_row_z(s), y = convert_row_y();
+    const uint4* row = reinterpret_cast<const uint4*>(sm.tile.ring[s & 1]) + ((z & 7) * 32 + y) * 4;
     uint4 q[4];
     uint32_t slab_or = 0, slab_and = kFull;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        q[k] = slab[tid + k * kThreads];
+        q[k] = row[(k + j) & 3];
         slab_or |= q[k].x | q[k].y | q[k].z | q[k].w;
         slab_and &= q[k].x & q[k].y & q[k].z & q[k].w;
     }
@@ -837,21 +839,13 @@ __device__ __forceinline__ void convert_ring_slab_c(SmemC& sm, int s, uint32_t& 
     uint32_t ob = 0;
     if (__all_sync(kFull, same)) {
         ob = slab_or ? kFull : 0u;
-        o_and &= ob & 0xFFu;
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t bits = nz8(q[k]);
-            o_and &= bits;
-            ob |= bits << (8 * k);
-        }
+        for (int k = 0; k < 4; ++k) ob |= nz8(q[k]) << (8 * k);
+        ob = __funnelshift_l(ob, ob, 8u * (uint32_t)j);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int idx = tid + k * kThreads;
-        const int row = s * 256 + (idx >> 2), p = idx & 3;      // row = z*32 + y
-        occ_bytes[(((row >> 5) + 1) * 34 + (row & 31) + 1) * 4 + p] = (unsigned char)(ob >> (8 * k));
-    }
+    o_and &= ob;
+    sm.occ[(z + 1) * 34 + y + 1] = ob;
 }
 
 // One packed block scan gives every thread its first ordinal and its slot in the word list; the non-empty words are
@@ -961,7 +955,7 @@ __device__ __forceinline__ void mesh_chunk_c(SmemC& sm, const uint16_t* __restri
     prof.mark(0);
     ChunkFlags fl;
     fl.any_solid = __syncthreads_or(v_or != 0u);        // barrier: occupancy interior published, ring dead
-    fl.all_solid = __syncthreads_and((o_and & 0xFFu) == 0xFFu);
+    fl.all_solid = __syncthreads_and(o_and == kFull);
     fl.single_id = fl.small_ids = false;
     prof.mark(1);
     if (bnd.tags) publish_boundary(sm, bnd, chunk, fl);
