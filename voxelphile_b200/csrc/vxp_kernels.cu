@@ -83,11 +83,13 @@ __global__ void __launch_bounds__(kThreads) pattern_fill_kernel(const vxp_coord*
 // caller and leaves the launch counters zeroed for the next call.
 //   column_insert_kernel   one thread per chunk: find-or-insert (cx,cz) in an open-addressing hash table
 //                          (atomicCAS on 64-bit keys); the inserting thread draws the column's id
-//   column_heights_kernel  persistent CTAs, one column at a time: lattice gradients, 34x34 heights, min / max
+//   column_heights_kernel  persistent CTAs, one column at a time: lattice gradients, 34x34 heights, min / max, column
+//                          tops per 32-layer band
 //   column_classify_kernel one thread per chunk: chunks entirely above / below the surface (most of a world) are
-//                          finished here, the others go on a work list
-//   terrain_mesh_kernel    persistent CTAs draw work items from a ticket counter, generate the chunk slab by slab
-//                          into the ring of vxp_mesh.cuh and run its pipeline; voxels never reach HBM.
+//                          finished here, the others go on a work list (the ones with many column tops at its front)
+//   terrain_mesh_kernel    persistent CTAs draw work items from a ticket counter, turn the heights of the footprint
+//                          straight into occupancy / equality words (masks_from_heights_g) and run the emit pipeline
+//                          of vxp_mesh.cuh; voxels never exist.
 constexpr int kColStride = 34 * 34 + 12;           // shorts per column record: footprint, hmin, hmax, kColBands band counts, 2 pad (8-byte multiple)
 constexpr int kColBands = 8;                       // band b = chunk layer (hmin >> 5) + b: how many of the footprint's columns end in it
 #ifndef VXP_HEAVY_MIN

@@ -4,12 +4,14 @@
 // has been converted); nothing needs the voxels once the occupancy bits and the id bit planes are out, so what a
 // CTA keeps is small and several CTAs share an SM (greedy: four, culled: five):
 //
-//   ring           ->  greedy: X-plane face masks, transposed equality rows of the X planes, staging / sweep log
-//                      culled: window of non-empty face words, staging
-//   eq   (12.4 KiB)    greedy: id planes (registers while streaming, stored for the chunks that use them);
-//                      the equality rows EX / EY / EZ afterwards (in place)
-//   occ  (4.5 KiB)     occupancy with halo; the Y / Z plane face masks are derived from it on the fly
-//                      (M = occ & ~occ_neighbour: two loads instead of one stored word)
+//   ring (2 x 16 KiB) ->  greedy: X-plane face masks, transposed equality rows of the X planes, staging / sweep log
+//                         culled: window of non-empty face words, staging
+//   eq   (12.4 KiB)       greedy: id planes (registers while streaming, stored for the chunks that use them);
+//                         the equality rows EX / EY / EZ afterwards (in place)
+//   occ  (4.5 KiB)        occupancy with halo; the Y / Z plane face masks are derived from it on the fly
+//                         (M = occ & ~occ_neighbour: two loads instead of one stored word)
+//   greedy: eq, the carry of the second pass and the row tables are dead while the chunk streams: a third ring buffer
+//   lies over them, so three of the four slabs are in flight from the start.
 //
 // Greedy chunks whose ids do not fit the id planes stream a second time (L2 hits) and compute their equality
 // rows per voxel, slab by slab.  Halo exchange, quad-record store and launch chaining: vxp_mesh_common.cuh.
