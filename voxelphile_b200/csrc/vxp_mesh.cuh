@@ -394,6 +394,7 @@ __device__ __forceinline__ uint32_t sweep_rows_g(const SweepG& st) {
     for (int v = 0; v < 32; ++v) rm |= (uint32_t)(st.m.row(v) != 0) << v;
     return rm;
 }
+template <bool kStore = true>
 __device__ __forceinline__ uint32_t sweep_log_g(SweepG& st, uint32_t rm, uint32_t plane, uint2* entry) {
     uint32_t births = 0;
     uint32_t todo = rm | (rm << 1);
@@ -420,7 +421,7 @@ __device__ __forceinline__ uint32_t sweep_log_g(SweepG& st, uint32_t rm, uint32_
             st.S = (st.S & Cs) | NS;
             st.E = (st.E & Cs) | NE;
             st.C = Mv;
-            if (Mv) *entry++ = make_uint2(Cs, plane << 5 | (uint32_t)v | births << 13);
+            if (kStore && Mv) *entry++ = make_uint2(Cs, plane << 5 | (uint32_t)v | births << 13);
             births += __popc(NS);
         }
         v = vn; valid = validn; Mv = Mn; Hv = Hn; Vv = Vn;
@@ -467,7 +468,7 @@ __device__ __forceinline__ void stage_births_g(const SmemG& sm, bool with_eq, co
 // a window of at least 1024 records below it, and each group is staged and flushed window by window before the next
 // one is swept (the V rows stay alive, so the records cannot spill into them).  The chunk's range has been reserved and
 // published by the caller; ordinals run on across the groups.  Returns false, having done nothing, if a half does not
-// fit either (the caller's stepped sweep takes those: 130 k cycles for a terrain chunk against 40 k this way).
+// fit either (the caller's stepped sweep takes those; for a terrain chunk it costs a quarter more than this way).
 template <class IdFn>
 __device__ __forceinline__ bool emit_greedy_halves(SmemG& sm, bool with_eq, const MeshOut& out, IdFn id_of) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -627,13 +628,14 @@ __device__ __forceinline__ void emit_greedy(SmemG& sm, uint32_t mi, bool with_eq
             return;
         }
     } else {
-        __syncthreads();                              // cursor = 0 published
-        if (tid < 192) {
-#pragma unroll 1
-            for (int v = 0; v <= 32; ++v) sweep_step_g(st, v, staging, 0u, &sm.cursor);
-        }
+        // the log does not fit: count the quads with a sweep that logs nothing (every run that starts is one), then emit by halves
+        uint32_t births = 0;
+        if (tid < 192) births = sweep_log_g<false>(st, rm, (uint32_t)tid, nullptr);
+        const uint32_t incl = warp_incl_scan(births, lane);
+        if (lane == 31) sm.scratch[warp] = incl;
         __syncthreads();
-        Q = sm.cursor;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) Q += sm.scratch[w];
         if (tid == 0) f = reserve_quads(sm, out, Q);
     }
     // the log or the records do not fit: the planes in two halves if that fits, else a stepped sweep that stages
