@@ -182,10 +182,11 @@ __device__ __forceinline__ void publish_boundary(const SM& sm, const Bnd& bnd, u
 // thread) whether any halo bit this thread produced is air.  Contains no barrier.
 // nb = neighbour index of face f = warp index (loaded by the caller before the tile wait).
 #ifndef VXP_PLANE_POLLS
-#define VXP_PLANE_POLLS 8
+#define VXP_PLANE_POLLS 16
 #endif
 constexpr int kPlanePolls = VXP_PLANE_POLLS;   // bounded re-reads of a boundary plane that is not there yet (never a wait-for);
-                                               // measured on config 2: 1 -> 109.4 us, 3 -> 104.9, 6 -> 104.1, 12 -> 103.5
+                                               // measured on config 2: round 1 (tile kernel) 1 -> 109.4 us, 3 -> 104.9, 6 -> 104.1, 12 -> 103.5;
+                                               // round 2: 4 -> 67.6, 8 -> 66.6, 16 -> 66.0, 32 / 64 -> 65.9
 // The halo is produced in two steps so that callers with something else to do can put it between them:
 // halo_begin   warps 2..5 write their +-Y / +-Z halo rows; warps 0,1 issue the first read of their x
 //              neighbour's tag and boundary plane (two loads in flight together, not waited for)
