@@ -873,8 +873,8 @@ def test_downsample_and_mesh_lod(mesher):
 def test_terrain_fill_large_batches_bit_exact(mesher):
     """Batches of >= 16 384 chunks take the shared-column path of vxp_terrain_fill_batch: one batch of 17 216 chunks
     made of a tall block (16 chunks per column), a flat sheet (every column its own) and a shuffled list with
-    negative coordinates (some columns shared with the block), against the oracle; then a smaller batch (direct
-    path) on the same context, and the large one again (next epoch of the column table)."""
+    negative coordinates (some columns shared with the block), against the oracle; then smaller batches (the
+    one-launch shared path) on the same context, and the large one again (next epoch of the column table)."""
     import torch
     from voxelphile_b200 import grid_coords
     rng = np.random.default_rng(13)
@@ -894,6 +894,14 @@ def test_terrain_fill_large_batches_bit_exact(mesher):
         small = mesher.terrain_fill(dev(coords[:1000]), seed)
         torch.cuda.synchronize()
         assert np.array_equal(small.cpu().numpy().view(np.uint16), want[:1000])
+        # 256 .. 16 383 chunks: one launch, the first chunk of a column computes its heights for the others
+        # (stacked, flat and shuffled columns in one batch; twice in a row: next epoch of the table)
+        pick = np.concatenate([np.arange(9216, 9216 + 1500), np.arange(12816, 12816 + 2500), np.arange(0, 2000)])
+        for again in range(2):
+            mid = mesher.terrain_fill(dev(coords[pick]), seed)
+            torch.cuda.synchronize()
+            assert np.array_equal(mid.cpu().numpy().view(np.uint16), want[pick]), (rep, again)
+            del mid
     # the fused path right after the column fill (they share the column scratch and its launch counters)
     fc = grid_coords((0, 6, 0), (3, 10, 2))
     wh, wc = O.terrain_world_hash(42, (0, 6, 0), (3, 10, 2), 1)

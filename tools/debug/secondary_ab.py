@@ -18,6 +18,9 @@ def timed(fn, steps):
 res = {}
 res["fill_us"] = timed(lambda s: m.terrain_fill(dc, 100 + s, out=vox[s % 4]), 100)
 vox = [m.terrain_fill(dc, 42 + k) for k in range(4)]
+sheet = torch.from_numpy(grid_coords((0, 8, 0), (64, 9, 64))).cuda()     # every chunk its own column
+res["fill_sheet_us"] = timed(lambda s: m.terrain_fill(sheet, 100 + s, out=vox[s % 4]), 100)
+vox = [m.terrain_fill(dc, 42 + k) for k in range(4)]
 res["fill_hash"] = hashlib.sha1(vox[1].cpu().numpy().tobytes()).hexdigest()[:12]
 res["pack_us"] = timed(lambda s: m.pack(vox[s % 4]), 40)
 pk, po, pt = m.pack(vox[0]); outs = [torch.empty_like(vox[0]) for _ in range(4)]

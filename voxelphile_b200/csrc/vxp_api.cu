@@ -328,11 +328,13 @@ vxp_status column_scratch(vxp_ctx* ctx, uint32_t n, vxp::ColumnScratch* out) {
         ctx->columns.mask = (uint32_t)(slots - 1);
         ctx->columns.epoch = 0;
         VXP_CUDA(ctx, cudaMemsetAsync(ctx->columns.keys, 0, b_keys, ctx->stream));
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->columns.id_of_slot, 0, b_ids, ctx->stream));
         VXP_CUDA(ctx, cudaMemsetAsync(ctx->columns.count, 0, b_cnt, ctx->stream));
         ctx->columns_cap = want;
     }
     if (++ctx->columns.epoch >= 1024u) {
         VXP_CUDA(ctx, cudaMemsetAsync(ctx->columns.keys, 0, ((size_t)ctx->columns.mask + 1) * 8, ctx->stream));
+        VXP_CUDA(ctx, cudaMemsetAsync(ctx->columns.id_of_slot, 0, ((size_t)ctx->columns.mask + 1) * 4, ctx->stream));   // epoch-stamped ready words (shared fill)
         ctx->columns.epoch = 1;
     }
     *out = ctx->columns;
@@ -346,6 +348,11 @@ vxp_status column_scratch(vxp_ctx* ctx, uint32_t n, vxp::ColumnScratch* out) {
 #define VXP_COLUMN_FILL_MIN 16384
 #endif
 constexpr uint32_t kColumnFillMin = VXP_COLUMN_FILL_MIN;
+// ... and from this many chunks up to there, through the one-launch variant of the same idea (terrain_fill_shared_kernel)
+#ifndef VXP_SHARED_FILL_MIN
+#define VXP_SHARED_FILL_MIN 256
+#endif
+constexpr uint32_t kSharedFillMin = VXP_SHARED_FILL_MIN;
 
 bool valid_mode(vxp_mode m) { return m == VXP_MODE_CULLED || m == VXP_MODE_GREEDY; }
 
@@ -615,6 +622,14 @@ vxp_status vxp_terrain_fill_batch(vxp_ctx* ctx, const vxp_coord* d_coords, uint3
         if (s != VXP_OK) return s;
         VXP_CUDA(ctx, vxp::launch_terrain_fill_columns(d_coords, n, seed, d_voxels, cols, ctx->stream));
         ctx->launches += 3;
+        return VXP_OK;
+    }
+    if (n >= kSharedFillMin) {   // one launch; the first chunk of a column computes its heights for the others
+        vxp::ColumnScratch cols{};
+        const vxp_status s = column_scratch(ctx, n, &cols);
+        if (s != VXP_OK) return s;
+        VXP_CUDA(ctx, vxp::launch_terrain_fill_shared(d_coords, n, seed, d_voxels, cols, ctx->stream));
+        ctx->launches += 1;
         return VXP_OK;
     }
     VXP_CUDA(ctx, vxp::launch_terrain_fill(d_coords, n, seed, d_voxels, ctx->stream));

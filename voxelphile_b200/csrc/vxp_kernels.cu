@@ -262,6 +262,110 @@ __global__ void __launch_bounds__(kThreads) terrain_fill_columns_kernel(const vx
     }
 }
 
+// Terrain fill of a small or medium batch, one launch: the first chunk of a column (cx,cz) to arrive claims the column in
+// the hash table (the same epoch-stamped find-or-insert as column_insert_kernel), computes its 32 x 32 heights - the noise
+// is 45 % of a chunk's instructions - and publishes them; the other chunks of the column wait for that word and read
+// 2 KiB from L2 instead.  A chunk only ever waits for a CTA that is already running (it has made the claim), so nobody
+// can be waiting for a CTA that has not been scheduled.  The ready word (cs.id_of_slot[slot]) is epoch << 22 | (id + 1).
+// Leaves cs.count zeroed (the last CTA out), like the fused mesh kernel.
+constexpr int kReadyIdBits = 22;
+__global__ void __launch_bounds__(kThreads) terrain_fill_shared_kernel(const vxp_coord* __restrict__ coords, uint32_t n, uint64_t seed,
+                                                                        ColumnScratch cs, uint32_t stride, uint16_t* __restrict__ out) {
+    __shared__ TerrainLattice s_lat;
+    __shared__ short s_h[1024];
+    __shared__ short s_zmin[32], s_zmax[32];
+    __shared__ uint32_t s_col[2];                      // column id, producer?
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // CTA b takes chunk (b * stride) mod n (stride coprime to n): the chunks of a column, neighbours in a sorted batch,
+    // arrive far apart in time, so all but the first find the heights there instead of waiting for them together
+    const uint32_t chunk = (uint32_t)(((unsigned long long)blockIdx.x * stride) % n);
+    const vxp_coord c = coords[chunk];
+    uint32_t slot = 0;
+    if (tid == 0) {
+        const unsigned long long key = column_key(c.x, c.z, cs.epoch);
+        slot = (uint32_t)(((key << 10) * 0x9E3779B97F4A7C15ull) >> 32) & cs.mask;
+        bool mine = false;
+        for (;;) {
+            unsigned long long old = mesh::ld_relaxed_u64(cs.keys + slot);
+            if ((old >> kKeyEpochShift) != cs.epoch) {   // a key of an earlier call (or none): the slot is free
+                const unsigned long long seen = atomicCAS(cs.keys + slot, old, key);
+                if (seen == old) { mine = true; break; }
+                old = seen;
+            }
+            if (old == key) break;
+            slot = (slot + 1) & cs.mask;
+        }
+        uint32_t id;
+        if (mine) {
+            id = atomicAdd(cs.count, 1u);
+        } else {                                         // the claimant is running: its heights are on their way
+            uint32_t w;
+            while (((w = mesh::ld_relaxed_u32(cs.id_of_slot + slot)) >> kReadyIdBits) != cs.epoch) __nanosleep(100);
+            __threadfence();                             // the heights were written before the word
+            id = (w & ((1u << kReadyIdBits) - 1u)) - 1u;
+        }
+        s_col[0] = id;
+        s_col[1] = mine ? 1u : 0u;
+    }
+    __syncthreads();
+    const uint32_t id = s_col[0];
+    const bool mine = s_col[1] != 0u;                    // block-uniform
+    short* col = cs.heights + (size_t)id * kColStride;   // this path keeps the 32 x 32 interior heights at the record's start
+    if (mine) {
+        const TerrainKeys tk = terrain_keys(seed);
+        terrain_lattice_fill(s_lat, tk, 32 * c.x, 32 * c.z);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int z = warp + k * kWarps;             // a warp owns the 32 columns of one z-layer
+            const int h = terrain_height_lattice(s_lat, 32 * c.x + lane, 32 * c.z + z);
+            s_h[z * 32 + lane] = (short)h;
+            col[z * 32 + lane] = (short)h;
+        }
+        __syncthreads();                                 // every height has been stored ...
+        if (tid == 0) {
+            __threadfence();                             // ... and is visible before the word that says so
+            mesh::st_relaxed_u32(cs.id_of_slot + slot, cs.epoch << kReadyIdBits | (id + 1u));
+        }
+    } else {
+        for (int i = tid; i < 512; i += kThreads)        // 2 KiB, 4 bytes at a time, past L1 (written during this launch)
+            reinterpret_cast<uint32_t*>(s_h)[i] = __ldcg(reinterpret_cast<const uint32_t*>(col) + i);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int z = warp + k * kWarps;
+        const int h = s_h[z * 32 + lane];
+        const int lo = __reduce_min_sync(kFull, h), hi = __reduce_max_sync(kFull, h);
+        if (lane == 0) { s_zmin[z] = (short)lo; s_zmax[z] = (short)hi; }
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)chunk * VXP_CHUNK_VOXELS);
+    const int Y0 = 32 * c.y;
+#pragma unroll 4
+    for (int j = tid; j < 4096; j += kThreads) {         // j = (z*32 + y)*4 + p
+        const int z = j >> 7, Y = Y0 + ((j >> 2) & 31), x0 = (j & 3) * 8;
+        uint4 v;
+        if (Y > s_zmax[z]) {                             // above every column of this layer: air
+            v = make_uint4(0, 0, 0, 0);
+        } else if (Y < s_zmin[z] - 3) {                  // below the dirt of every column: stone / slate by Y only
+            const uint32_t b = ((Y >> 3) & 1) ? 4u : 3u, bb = b | b << 16;
+            v = make_uint4(bb, bb, bb, bb);
+        } else {
+            const short* hp = s_h + z * 32 + x0;
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = terrain_block(hp[2 * e], Y) | terrain_block(hp[2 * e + 1], Y) << 16;
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        st_voxels16(dst + j, v);
+    }
+    if (tid == 0 && atomicAdd(cs.count + 3, 1u) == gridDim.x - 1) {   // last CTA out: leave the counters zeroed
+        cs.count[0] = 0u;
+        cs.count[3] = 0u;
+    }
+}
+
 // ---- one surface chunk: footprint -> occupancy / equality words, no voxels in between.
 // A terrain column (x, z) is a function of y alone: solid up to its height, grass on top, three layers of dirt, then stone
 // and slate in bands of eight.  So the 32 voxels of a column are four words with bit y set - occupancy and the three id
@@ -534,6 +638,16 @@ cudaError_t launch_terrain_fill(const vxp_coord* d_coords, uint32_t n, uint64_t 
                                 cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     terrain_fill_kernel<<<n, kThreads, 0, stream>>>(d_coords, n, seed, d_voxels);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_terrain_fill_shared(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
+                                       const ColumnScratch& cs, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    uint32_t stride = (uint32_t)(0.6180339887 * n) | 1u;   // the batch in golden-ratio steps
+    auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+    while (gcd(stride, n) != 1u) stride += 2;
+    terrain_fill_shared_kernel<<<n, kThreads, 0, stream>>>(d_coords, n, seed, cs, stride % n, d_voxels);
     return cudaGetLastError();
 }
 

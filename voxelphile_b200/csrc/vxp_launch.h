@@ -44,6 +44,9 @@ size_t column_record_bytes();
 cudaError_t configure_device();
 cudaError_t launch_terrain_fill(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
                                 cudaStream_t stream);
+// one launch; the chunks of a column share its heights through the column scratch (n <= 2^22 - 2)
+cudaError_t launch_terrain_fill_shared(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
+                                       const ColumnScratch& cs, cudaStream_t stream);
 // Large batches: the chunks of a column (cx,cz) share one height footprint (three launches; columns: scratch for n chunks).
 cudaError_t launch_terrain_fill_columns(const vxp_coord* d_coords, uint32_t n, uint64_t seed, uint16_t* d_voxels,
                                         const ColumnScratch& columns, cudaStream_t stream);
