@@ -14,7 +14,7 @@ cap() {  # name target regex
 cap greedy greedy mesh_kernel_g
 cap culled culled mesh_kernel_c
 cap fused fused_greedy terrain_mesh_kernel
-cap fill fill terrain_fill_kernel
+cap fill fill terrain_fill
 cap pack pack ^pack_chunks
 cap unpack unpack unpack_chunks
 cap lod lod downsample
