@@ -797,8 +797,7 @@ vxp_status vxp_terrain_fill_host(vxp_ctx* ctx, const vxp_coord* coords, uint32_t
     ctx->chain_open = false;
     VXP_CUDA(ctx, cudaMemcpyAsync(ctx->d_coords, coords, (size_t)n * sizeof(vxp_coord), cudaMemcpyHostToDevice,
                                   ctx->stream));
-    VXP_CUDA(ctx, vxp::launch_terrain_fill(ctx->d_coords, n, seed, ctx->d_voxels, ctx->stream));
-    ctx->launches += 1;
+    if ((s = vxp_terrain_fill_batch(ctx, ctx->d_coords, n, seed, ctx->d_voxels)) != VXP_OK) return s;   // picks the path by batch size
     VXP_CUDA(ctx, cudaMemcpyAsync(voxels, ctx->d_voxels, (size_t)n * VXP_CHUNK_VOXELS * sizeof(uint16_t),
                                   cudaMemcpyDeviceToHost, ctx->stream));
     VXP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
