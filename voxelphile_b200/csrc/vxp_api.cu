@@ -115,7 +115,7 @@ struct vxp_ctx {
     uint64_t* h_verts = nullptr;    uint32_t* h_indices = nullptr; size_t h_quads_cap = 0;
     uint64_t* h_total = nullptr;
     // host-level pipeline (vxp_mesh_chunks_host): copy streams, per-slice events and running totals
-    static constexpr int kMaxSlices = 8;
+    static constexpr int kMaxSlices = 16;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
     uint64_t* h_totals = nullptr;   // pinned, kMaxSlices entries
@@ -830,7 +830,9 @@ vxp_status vxp_mesh_chunks_host(vxp_ctx* ctx, const uint16_t* voxels, const int3
     uint64_t total = 0;
     bool done = false;
     if (n) {
-        const uint32_t S = n >= 2048 ? 8u : n >= 256 ? 4u : 1u;
+        // more, smaller slices shorten the part of the call that nothing overlaps (the last slice's kernel and download);
+        // measured on 4096 chunks: 8 slices 774 k chunks/s, 16: 786 k, 32: 766 k
+        const uint32_t S = n >= 4096 ? 16u : n >= 2048 ? 8u : n >= 256 ? 4u : 1u;
         const uint32_t slice = (n + S - 1) / S;
         // slice whose upload completes the inputs of slice k
         uint32_t need[vxp_ctx::kMaxSlices];
